@@ -1,0 +1,86 @@
+#include "common.cuh"
+#include <cstring>
+#include <mutex>
+
+namespace gdn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime's entry-point query, so the library itself loads on a
+// machine without a driver (symbol-export checks on the CPU-only build box).
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GDN_CUDA_ERROR, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; i++) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    if (i > 0) s[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, ptr, d, s, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(GDN_CUDA_ERROR,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] ptr %p",
+                (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+                (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0),
+                (unsigned long long)(rank > 4 ? d[4] : 0), b[0], rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0,
+                rank > 3 ? b[3] : 0, rank > 4 ? b[4] : 0, ptr);
+  }
+  return GDN_OK;
+}
+
+}  // namespace gdn
+
+#define GDN_API __attribute__((visibility("default")))
+extern "C" {
+GDN_API const char* gdn_last_error(void) { return gdn::g_err; }
+GDN_API int gdn_version(void) { return 100; }
+GDN_API int gdn_sm_count(void) { return gdn::device_sm_count(); }
+}

@@ -1,0 +1,598 @@
+// Implicit-GEMM convolution for sm_100a: tcgen05.mma (BF16 x BF16 -> FP32 in TMEM), TMA-staged NHWC tiles.
+//
+// One persistent CTA per SM, 7 warps:
+//   warps 0-3  epilogue  (TMEM -> registers -> bias / ReLU / residual / tanh / BN statistics -> global)
+//   warp  4    A producer (activations, TMA)
+//   warp  5    MMA issuer (one elected thread) + TMEM owner
+//   warp  6    B producer (weights, TMA)
+//
+// GEMM view: D[pixels(128), Cout tile(BN)] += A[pixels, 64 ch] * W[tap][Cout tile, 64 ch]^T over taps x 64-ch chunks.
+//
+// Two ways of staging A:
+//   HALO   (stride 1, large maps): one TMA box brings the tile's whole input halo
+//          [(16+kh-1) x (8J+kw-1)] pixels x 64 ch into smem ONCE per chunk; every tap then reads a shifted
+//          window of it through the UMMA descriptor (start address += (r*halo_w + s)*128 B, SBO = halo_w*128 B),
+//          so activations cross L2->smem once instead of kh*kw times.  J sub-tiles (16 rows x 8 cols = 128
+//          pixels each) share every weight tile.
+//   TAPBOX (anything: stride 2, 1x1 on a virtual concat of two sources, tiny maps): one TMA box per (tap, chunk).
+// (tools/probe_umma.cu is the hardware check of the descriptor semantics this relies on.)
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace gdn {
+
+constexpr int kThreads = 7 * 32;
+constexpr int kWarpA = 4, kWarpMMA = 5, kWarpB = 6;
+constexpr int kMaxA = 8, kMaxB = 8;
+
+struct ConvK {
+  int n_img, out_h, out_w;
+  int tiles_x, tiles_y, cout_blocks, total_tiles;
+  int mode, J;
+  int tw_log2, th_log2, nb;  // TAPBOX tile decode
+  int kh, kw, stride;
+  int chunks0, chunks1, c0_total, c1_total;
+  int off_y, off_x;          // buffer coordinates: in = out*stride + tap + off
+  int off_y1, off_x1;        // same for source 1
+  int halo_w;
+  uint32_t a_bytes;
+  int na, nbst, acc_bufs;
+  const float* bias;
+  int relu, tanh_out;
+  const float* resid;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ob_pad, ob_reflect;
+  int dst_h, dst_w, dst_sy, dst_sx, dst_oy, dst_ox;
+  int cout, cout_pad;
+  double* stat_sum;
+  double* stat_sq;
+};
+
+struct Ring {
+  int i = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next(int n) {
+    if (++i == n) {
+      i = 0;
+      ph ^= 1;
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Sum v[0..NV) over the 32 lanes; afterwards lane l holds the total of element l (valid for l < NV).
+template <int NV>
+__device__ __forceinline__ float lane_transpose_sum(float (&v)[NV], int lane) {
+  if (NV < 32) {
+    // fold lanes together first so that log2(NV) scatter steps remain
+#pragma unroll
+    for (int off = 16; off >= NV; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+  }
+#pragma unroll
+  for (int len = NV / 2; len >= 1; len >>= 1) {
+    const bool up = (lane & len) != 0;
+#pragma unroll
+    for (int i = 0; i < len; i++) {
+      float send = up ? v[i] : v[i + len];
+      float keep = up ? v[i + len] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, len);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const ConvK p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t B_BYTES = BN * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.na * p.a_bytes;
+
+  __shared__ uint64_t a_full[kMaxA], a_empty[kMaxA], b_full[kMaxB], b_empty[kMaxB], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_stat[2][BN >= 32 ? BN : 32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool halo = (p.mode == GDN_CONV_HALO);
+  const int chunks = p.chunks0 + p.chunks1;
+  const int taps = p.kh * p.kw;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxA; i++) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxB; i++) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 2 * (BN >= 32 ? BN : 32); i += kThreads) (&s_stat[0][0])[i] = 0.f;
+  __syncwarp();
+  if (warp == kWarpMMA) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  if (warp == kWarpA && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+  }
+  if (warp == kWarpB && lane == 0) tma_prefetch_desc(&tmB);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int acc_stride = p.J * BN;
+
+  auto decode = [&](int t, int& nblk, int& tx, int& ty, int& img) {
+    nblk = t % p.cout_blocks;
+    t /= p.cout_blocks;
+    tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    ty = t % p.tiles_y;
+    img = t / p.tiles_y;
+  };
+  const int tile_h = halo ? 16 : (1 << p.th_log2);
+  const int tile_w = halo ? 8 * p.J : (1 << p.tw_log2);
+
+  if (warp == kWarpA) {
+    // ------------------------------------------------------------------ A producer
+    if (lane == 0) {
+      Ring ra;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int nblk, tx, ty, img;
+        decode(t, nblk, tx, ty, img);
+        const int oy0 = ty * tile_h, ox0 = tx * tile_w, n0 = img * p.nb;
+        for (int c = 0; c < chunks; c++) {
+          const bool s1 = c >= p.chunks0;
+          const CUtensorMap* tm = s1 ? &tmA1 : &tmA0;
+          const int cc = s1 ? c - p.chunks0 : c;
+          const int offy = s1 ? p.off_y1 : p.off_y, offx = s1 ? p.off_x1 : p.off_x;
+          const int ctot = s1 ? p.c1_total : p.c0_total;
+          if (halo) {
+            mbar_wait(&a_empty[ra.i], ra.ph ^ 1);
+            mbar_expect_tx(&a_full[ra.i], p.a_bytes);
+            tma_load_4d(tm, &a_full[ra.i], sA + (size_t)ra.i * p.a_bytes, cc * 64, ox0 + offx, oy0 + offy, img);
+            ra.next(p.na);
+          } else {
+            for (int r = 0; r < p.kh; r++)
+              for (int s = 0; s < p.kw; s++) {
+                mbar_wait(&a_empty[ra.i], ra.ph ^ 1);
+                mbar_expect_tx(&a_full[ra.i], p.a_bytes);
+                uint8_t* dst = sA + (size_t)ra.i * p.a_bytes;
+                if (p.stride == 1) {
+                  tma_load_4d(tm, &a_full[ra.i], dst, cc * 64, ox0 + s + offx, oy0 + r + offy, n0);
+                } else {
+                  // 5D view (2C, Wp/2, 2, Hp/2, N): buffer x = 2*ox + s + off -> (x >> 1, x & 1)
+                  const int bx = s + offx, by = r + offy;
+                  const int fx = bx >> 1, px = bx & 1, fy = by >> 1, py = by & 1;  // arithmetic shift = floor
+                  tma_load_5d(tm, &a_full[ra.i], dst, px * ctot + cc * 64, ox0 + fx, py, oy0 + fy, n0);
+                }
+                ra.next(p.na);
+              }
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpB) {
+    // ------------------------------------------------------------------ B producer (weights)
+    if (lane == 0) {
+      Ring rb;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int nblk, tx, ty, img;
+        decode(t, nblk, tx, ty, img);
+        for (int c = 0; c < chunks; c++)
+          for (int tap = 0; tap < taps; tap++) {
+            mbar_wait(&b_empty[rb.i], rb.ph ^ 1);
+            mbar_expect_tx(&b_full[rb.i], B_BYTES);
+            tma_load_3d(&tmB, &b_full[rb.i], sB + (size_t)rb.i * B_BYTES, c * 64, nblk * BN, tap);
+            rb.next(p.nbst);
+          }
+      }
+    }
+  } else if (warp == kWarpMMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Ring ra, rb, rc;
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
+        tc_fence_after();
+        const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride);
+        for (int c = 0; c < chunks; c++) {
+          if (halo) {
+            mbar_wait(&a_full[ra.i], ra.ph);
+          }
+          for (int r = 0; r < p.kh; r++)
+            for (int s = 0; s < p.kw; s++) {
+              if (!halo) mbar_wait(&a_full[ra.i], ra.ph);
+              mbar_wait(&b_full[rb.i], rb.ph);
+              tc_fence_after();
+              const uint32_t a0 = sA_u + (uint32_t)ra.i * p.a_bytes + (halo ? (uint32_t)(r * p.halo_w + s) * 128u : 0u);
+              const uint32_t b0 = sB_u + (uint32_t)rb.i * B_BYTES;
+              const uint32_t first = (c == 0 && r == 0 && s == 0) ? 0u : 1u;
+              for (int j = 0; j < p.J; j++) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                  const uint64_t ad = make_smem_desc_sw128(a0 + (uint32_t)j * 1024u + k4 * 32u, 0, a_sbo);
+                  const uint64_t bd = make_smem_desc_sw128(b0 + k4 * 32u, 0, 1024u);
+                  umma_bf16(acc_addr + (uint32_t)(j * BN), ad, bd, idesc, first | (uint32_t)k4);
+                }
+              }
+              umma_commit(&b_empty[rb.i]);
+              rb.next(p.nbst);
+              if (!halo) {
+                umma_commit(&a_empty[ra.i]);
+                ra.next(p.na);
+              }
+            }
+          if (halo) {
+            umma_commit(&a_empty[ra.i]);
+            ra.next(p.na);
+          }
+        }
+        umma_commit(&acc_full[rc.i]);
+        rc.next(p.acc_bufs);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 0..3
+    constexpr int CW = BN >= 32 ? 32 : 16;  // columns per TMEM load
+    Ring rc;
+    const int q = warp;
+    const int m = q * 32 + lane;
+    const bool do_stats = p.stat_sum != nullptr;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int nblk, tx, ty, img;
+      decode(t, nblk, tx, ty, img);
+      mbar_wait(&acc_full[rc.i], rc.ph);
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride) + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < p.J; j++) {
+        int oy, ox, n;
+        if (halo) {
+          oy = ty * 16 + (m >> 3);
+          ox = tx * (8 * p.J) + 8 * j + (m & 7);
+          n = img;
+        } else {
+          const int tw = 1 << p.tw_log2, th = 1 << p.th_log2;
+          ox = tx * tw + (m & (tw - 1));
+          oy = ty * th + ((m >> p.tw_log2) & (th - 1));
+          n = img * p.nb + (m >> (p.tw_log2 + p.th_log2));
+        }
+        const bool valid = (oy < p.out_h) && (ox < p.out_w) && (n < p.n_img);
+        const int dy = oy * p.dst_sy + p.dst_oy, dx = ox * p.dst_sx + p.dst_ox;
+        const size_t pix = ((size_t)n * p.dst_h + dy) * p.dst_w + dx;
+        // destinations in the padded bf16 buffer (interior + reflection images)
+        int ys[3], xs[3], ny = 0, nx = 0;
+        if (p.out_bf16) {
+          const int P = p.ob_pad;
+          ys[ny++] = dy + P;
+          xs[nx++] = dx + P;
+          if (p.ob_reflect) {
+            if (dy >= 1 && dy <= P) ys[ny++] = P - dy;
+            if (dy >= p.dst_h - 1 - P && dy <= p.dst_h - 2) ys[ny++] = P + 2 * (p.dst_h - 1) - dy;
+            if (dx >= 1 && dx <= P) xs[nx++] = P - dx;
+            if (dx >= p.dst_w - 1 - P && dx <= p.dst_w - 2) xs[nx++] = P + 2 * (p.dst_w - 1) - dx;
+          }
+        }
+        const int Hp = p.dst_h + 2 * p.ob_pad, Wp = p.dst_w + 2 * p.ob_pad;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += CW) {
+          float v[CW];
+          {
+            uint32_t r[CW];
+            if constexpr (CW == 32) tmem_ld_32x32(acc_addr + (uint32_t)(j * BN + cc), r);
+            else tmem_ld_32x16(acc_addr + (uint32_t)(j * BN + cc), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CW; i++) v[i] = __uint_as_float(r[i]);
+          }
+          const int cb = nblk * BN + cc;
+          if (do_stats) {
+            float s1[CW], s2[CW];
+#pragma unroll
+            for (int i = 0; i < CW; i++) {
+              const float x = valid ? v[i] : 0.f;
+              s1[i] = x;
+              s2[i] = x * x;
+            }
+            const float t1 = lane_transpose_sum<CW>(s1, lane);
+            const float t2 = lane_transpose_sum<CW>(s2, lane);
+            if (lane < CW) {
+              atomicAdd(&s_stat[0][cc + lane], t1);
+              atomicAdd(&s_stat[1][cc + lane], t2);
+            }
+          }
+          if (valid) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < CW; i++)
+                if (cb + i < p.cout) v[i] += __ldg(p.bias + cb + i);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < CW; i++) v[i] = fmaxf(v[i], 0.f);
+            }
+            const bool full = (cb + CW <= p.cout);
+            if (p.resid) {
+              const float* rp = p.resid + pix * p.cout + cb;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < CW; i += 4) {
+                  const float4 rv = *reinterpret_cast<const float4*>(rp + i);
+                  v[i] += rv.x; v[i + 1] += rv.y; v[i + 2] += rv.z; v[i + 3] += rv.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < CW; i++)
+                  if (cb + i < p.cout) v[i] += rp[i];
+              }
+            }
+            if (p.tanh_out) {
+#pragma unroll
+              for (int i = 0; i < CW; i++) v[i] = tanhf(v[i]);
+            }
+            if (p.out_f32) {
+              float* op = p.out_f32 + pix * p.cout + cb;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < CW; i += 4)
+                  *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < CW; i++)
+                  if (cb + i < p.cout) op[i] = v[i];
+              }
+            }
+            if (p.out_bf16) {
+              uint32_t w[CW / 2];
+#pragma unroll
+              for (int i = 0; i < CW / 2; i++) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+              for (int a = 0; a < ny; a++)
+                for (int b = 0; b < nx; b++) {
+                  __nv_bfloat16* op = p.out_bf16 + (((size_t)n * Hp + ys[a]) * Wp + xs[b]) * p.cout + cb;
+                  if (full) {
+#pragma unroll
+                    for (int i = 0; i < CW / 2; i += 4)
+                      *reinterpret_cast<uint4*>(op + 2 * i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < CW; i++)
+                      if (cb + i < p.cout) op[i] = __float2bfloat16(v[i]);
+                  }
+                }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[rc.i]);
+      rc.next(p.acc_bufs);
+      if (do_stats && p.cout_blocks > 1) {
+        // the channel block changes from tile to tile: flush the per-CTA partials now (4 epilogue warps only)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x; i < BN; i += 128) {
+          atomicAdd(p.stat_sum + nblk * BN + i, (double)s_stat[0][i]);
+          atomicAdd(p.stat_sq + nblk * BN + i, (double)s_stat[1][i]);
+          s_stat[0][i] = 0.f;
+          s_stat[1][i] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    if (do_stats && p.cout_blocks == 1) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x; i < BN; i += 128) {
+        if (i < p.cout) {
+          atomicAdd(p.stat_sum + i, (double)s_stat[0][i]);
+          atomicAdd(p.stat_sq + i, (double)s_stat[1][i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMMA) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------- host side
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) l++;
+  return l;
+}
+
+static int make_act_map(CUtensorMap* tm, const gdn_act& a, int stride, const uint32_t* box4 /*c,w,h,n*/) {
+  const uint64_t Hp = a.h + 2 * a.pad, Wp = a.w + 2 * a.pad, C = a.c;
+  if (stride == 1) {
+    uint64_t dims[4] = {C, Wp, Hp, (uint64_t)a.n};
+    uint64_t str[3] = {C * 2, C * 2 * Wp, C * 2 * Wp * Hp};
+    return encode_tmap_bf16(tm, a.ptr, 4, dims, str, box4);
+  }
+  if ((Hp & 1) || (Wp & 1)) return fail(GDN_UNSUPPORTED_SHAPE, "stride-2 source needs even padded dims (%d x %d)", (int)Hp, (int)Wp);
+  uint64_t dims[5] = {2 * C, Wp / 2, 2, Hp / 2, (uint64_t)a.n};
+  uint64_t str[4] = {2 * C * 2, C * 2 * Wp, 2 * C * 2 * Wp, C * 2 * Wp * Hp};
+  uint32_t box[5] = {box4[0], box4[1], 1, box4[2], box4[3]};
+  return encode_tmap_bf16(tm, a.ptr, 5, dims, str, box);
+}
+
+template <int BN>
+static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvK& k, size_t smem,
+                  cudaStream_t st) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    configured[dev] = true;
+  }
+  int grid = k.total_tiles < device_sm_count() ? k.total_tiles : device_sm_count();
+  conv_igemm_kernel<BN><<<grid, kThreads, smem, st>>>(a0, a1, b, k);
+  GDN_LAUNCH_CHECK("conv_igemm_kernel");
+  return GDN_OK;
+}
+
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream) {
+  if (!d || !d->src0.ptr || !d->weights) return fail(GDN_INVALID_DESC, "gdn_conv2d: null descriptor / source / weights");
+  const bool two = d->src1.ptr != nullptr;
+  if (d->src0.c % 64 || (two && d->src1.c % 64))
+    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: input channels must be multiples of 64 (got %d, %d)", d->src0.c, two ? d->src1.c : 0);
+  if (d->stride != 1 && d->stride != 2) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: stride %d", d->stride);
+  if (d->cout_pad % 16 || d->cout > d->cout_pad) return fail(GDN_INVALID_DESC, "gdn_conv2d: cout %d / cout_pad %d", d->cout, d->cout_pad);
+  if (d->cout != d->cout_pad && d->cout_pad != 16) return fail(GDN_INVALID_DESC, "gdn_conv2d: padded cout only for the 16-wide head");
+  if (two && (d->src1.n != d->src0.n)) return fail(GDN_INVALID_DESC, "gdn_conv2d: source batch mismatch");
+  int BN = d->cout_pad >= 256 ? 256 : d->cout_pad;
+  if (BN != 16 && BN != 64 && BN != 128 && BN != 256) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout_pad %d", d->cout_pad);
+  if (d->cout_pad % BN) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout_pad %d not a multiple of %d", d->cout_pad, BN);
+  if (d->cout % 8 && d->cout != 1) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout %d", d->cout);
+
+  ConvK k{};
+  k.n_img = d->src0.n;
+  k.out_h = d->out_h;
+  k.out_w = d->out_w;
+  k.kh = d->kh;
+  k.kw = d->kw;
+  k.stride = d->stride;
+  k.chunks0 = d->src0.c / 64;
+  k.chunks1 = two ? d->src1.c / 64 : 0;
+  k.c0_total = d->src0.c;
+  k.c1_total = two ? d->src1.c : 0;
+  k.off_y = d->off_y + d->src0.pad;
+  k.off_x = d->off_x + d->src0.pad;
+  k.off_y1 = d->off_y + (two ? d->src1.pad : 0);
+  k.off_x1 = d->off_x + (two ? d->src1.pad : 0);
+  k.cout_blocks = d->cout_pad / BN;
+  k.bias = d->bias;
+  k.relu = d->relu;
+  k.tanh_out = d->tanh_out;
+  k.resid = d->resid;
+  k.out_f32 = d->out_f32;
+  k.out_bf16 = (__nv_bfloat16*)d->out_bf16.ptr;
+  k.ob_pad = d->out_bf16.ptr ? d->out_bf16.pad : 0;
+  k.ob_reflect = d->out_reflect;
+  k.dst_h = d->dst_h;
+  k.dst_w = d->dst_w;
+  k.dst_sy = d->dst_sy ? d->dst_sy : 1;
+  k.dst_sx = d->dst_sx ? d->dst_sx : 1;
+  k.dst_oy = d->dst_oy;
+  k.dst_ox = d->dst_ox;
+  k.cout = d->cout;
+  k.cout_pad = d->cout_pad;
+  k.stat_sum = d->stat_sum;
+  k.stat_sq = d->stat_sqsum;
+  if (d->out_bf16.ptr && (d->out_bf16.h != d->dst_h || d->out_bf16.w != d->dst_w || d->out_bf16.c != d->cout))
+    return fail(GDN_INVALID_DESC, "gdn_conv2d: out_bf16 extent %dx%dx%d != dst %dx%dx%d", d->out_bf16.h, d->out_bf16.w,
+                d->out_bf16.c, d->dst_h, d->dst_w, d->cout);
+  if ((k.out_h - 1) * k.dst_sy + k.dst_oy >= k.dst_h || (k.out_w - 1) * k.dst_sx + k.dst_ox >= k.dst_w)
+    return fail(GDN_INVALID_DESC, "gdn_conv2d: outputs fall outside the destination");
+  if (d->out_reflect && d->out_bf16.ptr && (d->out_bf16.pad >= d->dst_h || d->out_bf16.pad >= d->dst_w))
+    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: reflection border %d >= extent", d->out_bf16.pad);
+
+  int mode = d->algo;
+  const int taps = d->kh * d->kw;
+  if (mode == GDN_CONV_AUTO)
+    mode = (d->stride == 1 && !two && taps > 1 && d->out_h >= 16 && d->out_w >= 16) ? GDN_CONV_HALO : GDN_CONV_TAPBOX;
+  if (mode == GDN_CONV_HALO && (d->stride != 1 || two)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: HALO needs stride 1, one source");
+  k.mode = mode;
+
+  const size_t smem_budget = 227 * 1024 - 4096 - 1024;  // dynamic smem minus alignment slack
+  const uint32_t b_bytes = BN * 128;
+  CUtensorMap tmA0, tmA1, tmB;
+  int rc;
+  if (mode == GDN_CONV_HALO) {
+    int J = BN <= 64 ? 4 : 2;
+    // halve J while a quarter or more of the computed columns would fall outside the image
+    while (J > 1) {
+      const int cols = (d->out_w + 8 * J - 1) / (8 * J) * (8 * J);
+      if ((cols - d->out_w) * 4 >= cols) J /= 2; else break;
+    }
+    const int halo_h = 16 + d->kh - 1;
+    int halo_w = 8 * J + d->kw - 1;
+    if (halo_h > 256 || halo_w > 256) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: halo too large");
+    k.J = J;
+    k.halo_w = halo_w;
+    k.a_bytes = (uint32_t)halo_h * halo_w * 128;
+    k.na = (k.chunks0 > 1 && 2 * (size_t)k.a_bytes + 3 * b_bytes <= smem_budget) ? 2 : 1;
+    size_t rem = smem_budget - (size_t)k.na * k.a_bytes;
+    k.nbst = (int)(rem / b_bytes);
+    if (k.nbst > kMaxB) k.nbst = kMaxB;
+    if (k.nbst < 2) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: halo tile does not fit shared memory");
+    k.acc_bufs = (2 * J * BN <= 512) ? 2 : 1;
+    k.tiles_x = (d->out_w + 8 * J - 1) / (8 * J);
+    k.tiles_y = (d->out_h + 15) / 16;
+    k.nb = 1;
+    k.total_tiles = k.tiles_x * k.tiles_y * k.n_img * k.cout_blocks;
+    uint32_t box[4] = {64, (uint32_t)halo_w, (uint32_t)halo_h, 1};
+    if ((rc = make_act_map(&tmA0, d->src0, 1, box))) return rc;
+    tmA1 = tmA0;
+  } else {
+    int tw = 8;
+    while (tw > d->out_w && tw > 1) tw >>= 1;
+    int th = 128 / tw;
+    while (th / 2 >= d->out_h && th > 1) th >>= 1;
+    int nb = 128 / (tw * th);
+    k.J = 1;
+    k.tw_log2 = ilog2(tw);
+    k.th_log2 = ilog2(th);
+    k.nb = nb;
+    k.a_bytes = 128 * 128;
+    k.acc_bufs = (2 * BN <= 512) ? 2 : 1;
+    size_t per = k.a_bytes + b_bytes;
+    int st = (int)(smem_budget / per);
+    if (st > kMaxB) st = kMaxB;
+    if (st < 2) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: stage does not fit");
+    k.nbst = st;
+    k.na = st;
+    k.tiles_x = (d->out_w + tw - 1) / tw;
+    k.tiles_y = (d->out_h + th - 1) / th;
+    const int groups = (k.n_img + nb - 1) / nb;
+    k.total_tiles = k.tiles_x * k.tiles_y * groups * k.cout_blocks;
+    uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)nb};
+    if ((rc = make_act_map(&tmA0, d->src0, d->stride, box))) return rc;
+    if (two) {
+      if ((rc = make_act_map(&tmA1, d->src1, d->stride, box))) return rc;
+    } else {
+      tmA1 = tmA0;
+    }
+  }
+  {
+    const uint64_t cin_total = (uint64_t)d->src0.c + (two ? d->src1.c : 0);
+    uint64_t dims[3] = {cin_total, (uint64_t)d->cout_pad, (uint64_t)taps};
+    uint64_t str[2] = {cin_total * 2, cin_total * 2 * d->cout_pad};
+    uint32_t box[3] = {64, (uint32_t)BN, 1};
+    if ((rc = encode_tmap_bf16(&tmB, const_cast<void*>(d->weights), 3, dims, str, box))) return rc;
+  }
+  const size_t smem = (size_t)k.na * k.a_bytes + (size_t)k.nbst * b_bytes + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 16: return launch<16>(tmA0, tmA1, tmB, k, smem, st);
+    case 64: return launch<64>(tmA0, tmA1, tmB, k, smem, st);
+    case 128: return launch<128>(tmA0, tmA1, tmB, k, smem, st);
+    default: return launch<256>(tmA0, tmA1, tmB, k, smem, st);
+  }
+}
