@@ -1,0 +1,631 @@
+// HBM-bound helper kernels around the tensor-core convolutions (sm_100a):
+//   im2col for thin-channel layers, BatchNorm finalize / apply (+ReLU, residual, reflection halo, x2 bilinear
+//   upsample, zero dilation), BatchNorm backward (reduce + apply), gradient fold (adjoint of reflection padding /
+//   upsampling / dilation / channel slicing), weight pack / gradient unpack.
+// All tensors are NHWC; 8 bf16 (16 B) or 4 fp32 (16 B) per thread access, grid-stride loops.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace gdn {
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_grid(long long work) {
+  long long b = (work + kEwThreads - 1) / kEwThreads;
+  const long long cap = (long long)device_sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  // nn.ReflectionPad2d index map (no edge repeat); valid for |overshoot| < n
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+struct bf16x8 {
+  uint4 u;
+};
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// src: fp32 planar [N][C][H][W] (C <= 4).  dst: bf16 [N*H*W][kpad], k = (r*kw + s)*C + c, zero beyond kh*kw*C.
+__global__ void im2col_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C, int H,
+                              int W, int kh, int kw, int pad, int reflect, int kpad) {
+  const int kreal = kh * kw * C;
+  const int groups = kpad / 8;
+  const long long total = (long long)N * H * W * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < kreal) {
+        const int c = k % C, t = k / C;
+        const int s = t % kw, r = t / kw;
+        int yy = y + r - pad, xx = x + s - pad;
+        bool ok = true;
+        if (reflect) {
+          yy = reflect_idx(yy, H);
+          xx = reflect_idx(xx, W);
+        } else {
+          ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+        }
+        if (ok) v = __ldg(src + (((long long)n * C + c) * H + yy) * W + xx);
+      }
+      f[j] = v;
+    }
+    *reinterpret_cast<uint4*>(dst + pix * kpad + g * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- BN finalize
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sum[c] / count;
+  double var = sq[c] / count - m * m;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma[c], b = beta[c];
+  scale[c] = g * rstd;
+  shift[c] = b - (float)m * g * rstd;
+  mean_out[c] = (float)m;
+  rstd_out[c] = rstd;
+  if (running_mean) {
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- act forward
+struct ActFwd {
+  const __nv_bfloat16* src_bf16;  // [N][H][W][C]  (exactly one of src_bf16 / src_f32)
+  const float* src_f32;
+  const float* scale;             // per channel or NULL (identity)
+  const float* shift;
+  const float* resid;             // fp32 [N][H][W][C] or NULL
+  int relu;
+  int N, H, W, C;
+  float* out_f32;                 // [N][H][W][C] or NULL
+  __nv_bfloat16* out_bf16;        // [N][OH+2P][OW+2P][C] or NULL, OH = H*up (or 2H when dilate)
+  int P, reflect, up, dilate;     // up: 0 none, 1 bilinear x2 align_corners=False, 2 align_corners=True
+};
+
+__device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c8, float* v) {
+  if (a.src_bf16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(a.src_bf16 + pix * a.C + c8);
+    unpack8(u, v);
+  } else {
+    const float4 p0 = *reinterpret_cast<const float4*>(a.src_f32 + pix * a.C + c8);
+    const float4 p1 = *reinterpret_cast<const float4*>(a.src_f32 + pix * a.C + c8 + 4);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+  }
+  if (a.scale) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], __ldg(a.scale + c8 + j), __ldg(a.shift + c8 + j));
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.resid) {
+    const float4 p0 = *reinterpret_cast<const float4*>(a.resid + pix * a.C + c8);
+    const float4 p1 = *reinterpret_cast<const float4*>(a.resid + pix * a.C + c8 + 4);
+    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+  }
+}
+
+// source coordinate + weight of F.interpolate(scale_factor=2, mode='bilinear')
+__device__ __forceinline__ void up_coord(int o, int in, int mode, int& i0, int& i1, float& w1) {
+  float src;
+  if (mode == 1) {
+    src = (o + 0.5f) * 0.5f - 0.5f;
+    if (src < 0.f) src = 0.f;
+  } else {
+    src = in > 1 ? o * (float)(in - 1) / (float)(2 * in - 1) : 0.f;
+  }
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  w1 = src - (float)i0;
+}
+
+__global__ void act_forward_kernel(const ActFwd a) {
+  const int cg = a.C / 8;
+  const long long n_f32 = a.out_f32 ? (long long)a.N * a.H * a.W * cg : 0;
+  const int OH = (a.up || a.dilate) ? 2 * a.H : a.H, OW = (a.up || a.dilate) ? 2 * a.W : a.W;
+  const int Hp = OH + 2 * a.P, Wp = OW + 2 * a.P;
+  const long long n_b16 = a.out_bf16 ? (long long)a.N * Hp * Wp * cg : 0;
+  const long long total = n_f32 > n_b16 ? n_f32 : n_b16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_f32) {
+      const int c8 = (int)(i % cg) * 8;
+      const long long pix = i / cg;
+      float v[8];
+      act_value8(a, pix, c8, v);
+      float* o = a.out_f32 + pix * a.C + c8;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (i < n_b16) {
+      const int c8 = (int)(i % cg) * 8;
+      long long t = i / cg;
+      const int xp = (int)(t % Wp);
+      t /= Wp;
+      const int yp = (int)(t % Hp);
+      const int n = (int)(t / Hp);
+      int Y = yp - a.P, X = xp - a.P;
+      bool inside = (Y >= 0 && Y < OH && X >= 0 && X < OW);
+      if (!inside && !a.reflect) continue;  // non-reflect borders are never read as data (TMA zero fill is used instead)
+      Y = reflect_idx(Y, OH);
+      X = reflect_idx(X, OW);
+      float v[8];
+      if (a.dilate) {
+        if ((Y & 1) || (X & 1)) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) v[j] = 0.f;
+        } else {
+          act_value8(a, ((long long)n * a.H + (Y >> 1)) * a.W + (X >> 1), c8, v);
+        }
+      } else if (a.up) {
+        int y0, y1, x0, x1;
+        float wy, wx;
+        up_coord(Y, a.H, a.up, y0, y1, wy);
+        up_coord(X, a.W, a.up, x0, x1, wx);
+        float v00[8], v01[8], v10[8], v11[8];
+        const long long base = (long long)n * a.H;
+        act_value8(a, (base + y0) * a.W + x0, c8, v00);
+        act_value8(a, (base + y0) * a.W + x1, c8, v01);
+        act_value8(a, (base + y1) * a.W + x0, c8, v10);
+        act_value8(a, (base + y1) * a.W + x1, c8, v11);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          // same association as ATen's upsample_bilinear2d: w(1-wy)*(row0 blend) + wy*(row1 blend)
+          const float top = (1.f - wx) * v00[j] + wx * v01[j];
+          const float bot = (1.f - wx) * v10[j] + wx * v11[j];
+          v[j] = (1.f - wy) * top + wy * bot;
+        }
+      } else {
+        act_value8(a, ((long long)n * a.H + Y) * a.W + X, c8, v);
+      }
+      *reinterpret_cast<uint4*>(a.out_bf16 + (((long long)n * Hp + yp) * Wp + xp) * a.C + c8) = pack8(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ BN backward
+struct BnBwd {
+  const float* dact;              // fp32 [N][H][W][C] gradient w.r.t. the activation output
+  const __nv_bfloat16* raw;       // bf16 [N][H][W][C] stored conv output (pre-BN)
+  const float* scale;             // gamma * rstd
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  int relu;
+  long long npix;
+  int C;
+  double* sum_g;                  // [C]
+  double* sum_gx;                 // [C]
+  // apply
+  __nv_bfloat16* dy;              // bf16 [N][H][W][C] (or dilated [N][2H][2W][C]) gradient w.r.t. the conv output
+  int H, W, dilate;
+  float* dgamma;                  // += sum_gx   (may be NULL)
+  float* dbeta;                   // += sum_g
+};
+
+
+// Per-channel reductions: threads are (pixel lane, 8-channel group) with the channel group fastest, so a warp
+// reads contiguous NHWC bytes.  Partials go block-level through shared-memory atomics, then one fp64 atomic per
+// channel per block.
+__global__ void bn_bwd_reduce_kernel(const BnBwd b) {
+  extern __shared__ float s_red[];  // [2][C]
+  const int cgs = b.C / 8;
+  const int lanes = blockDim.x / cgs;
+  const int g = threadIdx.x % cgs, pl = threadIdx.x / cgs;
+  for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  float sg[8], sx[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) sg[j] = sx[j] = 0.f;
+  if (pl < lanes) {
+    const int c8 = g * 8;
+    float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sc[j] = b.scale[c8 + j];
+      sh[j] = b.shift[c8 + j];
+      mu[j] = b.mean[c8 + j];
+      rs[j] = b.rstd[c8 + j];
+    }
+    for (long long pix = (long long)blockIdx.x * lanes + pl; pix < b.npix; pix += (long long)gridDim.x * lanes) {
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
+      const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
+      const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
+      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float gq = d[j];
+        if (b.relu && fmaf(x[j], sc[j], sh[j]) <= 0.f) gq = 0.f;
+        sg[j] += gq;
+        sx[j] += gq * (x[j] - mu[j]) * rs[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      atomicAdd(&s_red[c8 + j], sg[j]);
+      atomicAdd(&s_red[b.C + c8 + j], sx[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < b.C; i += blockDim.x) {
+    atomicAdd(b.sum_g + i, (double)s_red[i]);
+    atomicAdd(b.sum_gx + i, (double)s_red[b.C + i]);
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const BnBwd b) {
+  const int cg = b.C / 8;
+  const int OH = b.dilate ? 2 * b.H : b.H, OW = b.dilate ? 2 * b.W : b.W;
+  const long long N = b.npix / ((long long)b.H * b.W);
+  const long long total = N * OH * OW * cg;
+  const double inv_n = 1.0 / (double)b.npix;
+  if (b.dgamma && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
+      b.dgamma[c] += (float)(b.sum_gx[c]);
+      b.dbeta[c] += (float)(b.sum_g[c]);
+    }
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg) * 8;
+    long long t = i / cg;
+    const int X = (int)(t % OW);
+    t /= OW;
+    const int Y = (int)(t % OH);
+    const long long n = t / OH;
+    float o[8];
+    if (b.dilate && ((Y & 1) || (X & 1))) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = 0.f;
+    } else {
+      const int y = b.dilate ? (Y >> 1) : Y, x = b.dilate ? (X >> 1) : X;
+      const long long pix = (n * b.H + y) * b.W + x;
+      float xr[8];
+      unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
+      const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
+      const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
+      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int c = c8 + j;
+        const float sc = __ldg(b.scale + c), sh = __ldg(b.shift + c);
+        float gq = d[j];
+        if (b.relu && fmaf(xr[j], sc, sh) <= 0.f) gq = 0.f;
+        const float xh = (xr[j] - __ldg(b.mean + c)) * __ldg(b.rstd + c);
+        const float m1 = (float)(b.sum_g[c] * inv_n), m2 = (float)(b.sum_gx[c] * inv_n);
+        o[j] = sc * (gq - m1 - xh * m2);
+      }
+    }
+    *reinterpret_cast<uint4*>(b.dy + i * 8) = pack8(o);
+  }
+}
+
+// -------------------------------------------------------------------------------------------- fold grad
+struct FoldK {
+  const float* dpad;   // fp32 [N][OH+2P][OW+2P][ctot]: gradient w.r.t. the conv's input buffer
+  int ctot, c_off;
+  int N, H, W, C;      // source activation extent
+  int P, reflect, up, dilate;
+  float* dact;         // fp32 [N][H][W][C]
+  int accumulate;
+};
+
+__device__ __forceinline__ int mirror_set(int Y, int OH, int P, int reflect, int* out) {
+  int n = 0;
+  out[n++] = Y + P;
+  if (reflect) {
+    if (Y >= 1 && Y <= P) out[n++] = P - Y;
+    if (Y >= OH - 1 - P && Y <= OH - 2) out[n++] = P + 2 * (OH - 1) - Y;
+  }
+  return n;
+}
+
+__global__ void fold_grad_kernel(const FoldK f) {
+  const int cg = f.C / 4;
+  const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
+  const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
+  const long long total = (long long)f.N * f.H * f.W * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cg) * 4;
+    long long t = i / cg;
+    const int x = (int)(t % f.W);
+    t /= f.W;
+    const int y = (int)(t % f.H);
+    const int n = (int)(t / f.H);
+    // hi-res rows / cols fed by (y, x) and their weights
+    int Ys[4], Xs[4], ny = 0, nx = 0;
+    float wys[4], wxs[4];
+    if (f.up) {
+      for (int Y = 2 * y - 1; Y <= 2 * y + 2; Y++) {
+        if (Y < 0 || Y >= OH) continue;
+        int a0, a1;
+        float w1;
+        up_coord(Y, f.H, f.up, a0, a1, w1);
+        const float w = (a0 == y ? 1.f - w1 : 0.f) + (a1 == y ? w1 : 0.f);
+        if (w != 0.f) { Ys[ny] = Y; wys[ny++] = w; }
+      }
+      for (int X = 2 * x - 1; X <= 2 * x + 2; X++) {
+        if (X < 0 || X >= OW) continue;
+        int a0, a1;
+        float w1;
+        up_coord(X, f.W, f.up, a0, a1, w1);
+        const float w = (a0 == x ? 1.f - w1 : 0.f) + (a1 == x ? w1 : 0.f);
+        if (w != 0.f) { Xs[nx] = X; wxs[nx++] = w; }
+      }
+    } else {
+      Ys[0] = f.dilate ? 2 * y : y; wys[0] = 1.f; ny = 1;
+      Xs[0] = f.dilate ? 2 * x : x; wxs[0] = 1.f; nx = 1;
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < ny; a++) {
+      int my[3];
+      const int cy = mirror_set(Ys[a], OH, f.P, f.reflect, my);
+      for (int b = 0; b < nx; b++) {
+        int mx[3];
+        const int cx = mirror_set(Xs[b], OW, f.P, f.reflect, mx);
+        const float w = wys[a] * wxs[b];
+        for (int p = 0; p < cy; p++)
+          for (int q = 0; q < cx; q++) {
+            const float4 v = *reinterpret_cast<const float4*>(
+                f.dpad + (((long long)n * Hq + my[p]) * Wq + mx[q]) * f.ctot + f.c_off + c4);
+            acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
+          }
+      }
+    }
+    float* o = f.dact + (((long long)n * f.H + y) * f.W + x) * f.C + c4;
+    if (f.accumulate) {
+      const float4 v = *reinterpret_cast<const float4*>(o);
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    }
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// -------------------------------------------------------------------------------- weight pack / unpack
+// packed[t][a][b] (t = r*kw + s, a < A, b < B) <-> w[a*sa + b*sb + r'*sr + s'*ss], (r', s') flipped when flip.
+// For im2col'd layers (col_c > 0): packed[0][a][k], k = (r*kw + s)*col_c + c  <->  w[a*sa + c*sb + r*sr + s*ss].
+struct PackK {
+  int kh, kw, A, B, Apad, Bpad;
+  long long sa, sb, sr, ss;
+  int flip, col_c;
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
+                                    __nv_bfloat16* __restrict__ out, const PackK k) {
+  const int T = k.col_c ? 1 : k.kh * k.kw;
+  const long long total = (long long)T * k.Apad * k.Bpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % k.Bpad);
+    const int a = (int)((i / k.Bpad) % k.Apad);
+    const int t = (int)(i / ((long long)k.Bpad * k.Apad));
+    float v = 0.f;
+    if (a < k.A) {
+      if (k.col_c) {
+        const int c = b % k.col_c, tt = b / k.col_c;
+        if (tt < k.kh * k.kw) v = w[a * k.sa + c * k.sb + (tt / k.kw) * k.sr + (tt % k.kw) * k.ss];
+      } else if (b < k.B) {
+        int r = t / k.kw, s = t % k.kw;
+        if (k.flip) { r = k.kh - 1 - r; s = k.kw - 1 - s; }
+        v = w[a * k.sa + b * k.sb + r * k.sr + s * k.ss];
+      }
+      if (scale_a) v *= scale_a[a];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// grad[w index] (+)= packed_dw[t][b][a]   (wgrad layout: [tap][ci = b][co = a], co padded to Apad)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k, int accumulate) {
+  const int T = k.col_c ? 1 : k.kh * k.kw;
+  const long long total = (long long)T * k.B * k.A;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(i % k.A);
+    const int b = (int)((i / k.A) % k.B);
+    const int t = (int)(i / ((long long)k.A * k.B));
+    long long widx;
+    if (k.col_c) {
+      const int c = b % k.col_c, tt = b / k.col_c;
+      if (tt >= k.kh * k.kw) continue;
+      widx = a * k.sa + c * k.sb + (tt / k.kw) * k.sr + (tt % k.kw) * k.ss;
+    } else {
+      int r = t / k.kw, s = t % k.kw;
+      if (k.flip) { r = k.kh - 1 - r; s = k.kw - 1 - s; }
+      widx = a * k.sa + b * k.sb + r * k.sr + s * k.ss;
+    }
+    const float v = dw[((long long)t * k.Bpad + b) * k.Apad + a];
+    if (accumulate) grad[widx] += v; else grad[widx] = v;
+  }
+}
+
+// eval-mode BatchNorm folded into a per-channel scale / bias
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
+                               float* __restrict__ scale, float* __restrict__ bias, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = gamma[c] / sqrtf(rvar[c] + eps);
+  scale[c] = s;
+  bias[c] = beta[c] - rmean[c] * s;
+}
+
+}  // namespace gdn
+
+using namespace gdn;
+#define GDN_API extern "C" __attribute__((visibility("default")))
+
+GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, int kh, int kw, int pad, int reflect,
+                       int kpad, gdn_stream stream) {
+  if (!src || !dst || c < 1 || c > 4 || kpad % 64 || kh * kw * c > kpad)
+    return fail(GDN_INVALID_DESC, "gdn_im2col: bad arguments (c=%d kpad=%d)", c, kpad);
+  if (reflect && (pad >= h || pad >= w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_im2col: reflection pad %d >= extent", pad);
+  const long long work = (long long)n * h * w * (kpad / 8);
+  im2col_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad,
+                                                                      reflect, kpad);
+  GDN_LAUNCH_CHECK("im2col_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                            float* shift, float* mean, float* rstd, int c, gdn_stream stream) {
+  if (!sum || !sqsum || !gamma || !beta || !scale || !shift || !mean || !rstd || c < 1)
+    return fail(GDN_INVALID_DESC, "gdn_bn_finalize: null pointer");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, gamma, beta, eps, momentum,
+                                                                     running_mean, running_var, scale, shift, mean, rstd, c);
+  GDN_LAUNCH_CHECK("bn_finalize_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                        float* scale, float* bias, int c, gdn_stream stream) {
+  bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, rmean, rvar, eps, scale, bias, c);
+  GDN_LAUNCH_CHECK("bn_fold_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
+  if (!d || (!d->src_bf16 == !d->src_f32)) return fail(GDN_INVALID_DESC, "gdn_act_forward: exactly one source required");
+  if (d->c % 8) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_forward: channels %d not a multiple of 8", d->c);
+  if (d->up && d->dilate) return fail(GDN_INVALID_DESC, "gdn_act_forward: up and dilate are exclusive");
+  const int OH = (d->up || d->dilate) ? 2 * d->h : d->h, OW = (d->up || d->dilate) ? 2 * d->w : d->w;
+  if (d->reflect && (d->pad >= OH || d->pad >= OW)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_forward: reflection pad too large");
+  ActFwd a{};
+  a.src_bf16 = (const __nv_bfloat16*)d->src_bf16;
+  a.src_f32 = d->src_f32;
+  a.scale = d->scale;
+  a.shift = d->shift;
+  a.resid = d->resid;
+  a.relu = d->relu;
+  a.N = d->n; a.H = d->h; a.W = d->w; a.C = d->c;
+  a.out_f32 = d->out_f32;
+  a.out_bf16 = (__nv_bfloat16*)d->out_bf16;
+  a.P = d->pad; a.reflect = d->reflect; a.up = d->up; a.dilate = d->dilate;
+  const long long w1 = a.out_f32 ? (long long)a.N * a.H * a.W * (a.C / 8) : 0;
+  const long long w2 = a.out_bf16 ? (long long)a.N * (OH + 2 * a.P) * (OW + 2 * a.P) * (a.C / 8) : 0;
+  const long long work = w1 > w2 ? w1 : w2;
+  if (work == 0) return GDN_OK;
+  act_forward_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  GDN_LAUNCH_CHECK("act_forward_kernel");
+  return GDN_OK;
+}
+
+static int fill_bnbwd(const gdn_bn_bwd_desc* d, BnBwd& b) {
+  if (!d || !d->dact || !d->raw || !d->scale || !d->shift || !d->mean || !d->rstd || !d->sum_g || !d->sum_gx)
+    return fail(GDN_INVALID_DESC, "gdn_bn_bwd: null pointer");
+  if (d->c % 8 || d->c > 512 || (256 % (d->c / 8))) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_bn_bwd: channels %d", d->c);
+  b.dact = d->dact;
+  b.raw = (const __nv_bfloat16*)d->raw;
+  b.scale = d->scale; b.shift = d->shift; b.mean = d->mean; b.rstd = d->rstd;
+  b.relu = d->relu;
+  b.npix = (long long)d->n * d->h * d->w;
+  b.C = d->c;
+  b.sum_g = d->sum_g; b.sum_gx = d->sum_gx;
+  b.dy = (__nv_bfloat16*)d->dy;
+  b.H = d->h; b.W = d->w; b.dilate = d->dilate;
+  b.dgamma = d->dgamma; b.dbeta = d->dbeta;
+  return GDN_OK;
+}
+
+GDN_API int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream) {
+  BnBwd b{};
+  int rc = fill_bnbwd(d, b);
+  if (rc) return rc;
+  const int lanes = kEwThreads / (b.C / 8);
+  long long blocks = (b.npix + lanes - 1) / lanes;
+  const long long cap = (long long)device_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, 2 * b.C * sizeof(float), (cudaStream_t)stream>>>(b);
+  GDN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream) {
+  BnBwd b{};
+  int rc = fill_bnbwd(d, b);
+  if (rc) return rc;
+  if (!b.dy) return fail(GDN_INVALID_DESC, "gdn_act_backward: dy is NULL");
+  const long long work = b.npix * (b.dilate ? 4 : 1) * (b.C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+  GDN_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
+  if (!d || !d->dpad || !d->dact) return fail(GDN_INVALID_DESC, "gdn_fold_grad: null pointer");
+  if (d->c % 4 || d->ctot % 4 || d->c_off % 4) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: channel alignment");
+  if (d->up > 1) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: only the align_corners=False adjoint is implemented");
+  FoldK f{};
+  f.dpad = d->dpad; f.ctot = d->ctot; f.c_off = d->c_off;
+  f.N = d->n; f.H = d->h; f.W = d->w; f.C = d->c;
+  f.P = d->pad; f.reflect = d->reflect; f.up = d->up; f.dilate = d->dilate;
+  f.dact = d->dact; f.accumulate = d->accumulate;
+  const long long work = (long long)f.N * f.H * f.W * (f.C / 4);
+  fold_grad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(f);
+  GDN_LAUNCH_CHECK("fold_grad_kernel");
+  return GDN_OK;
+}
+
+static void fill_pack(const gdn_pack_desc* d, PackK& k) {
+  k.kh = d->kh; k.kw = d->kw; k.A = d->a; k.B = d->b; k.Apad = d->a_pad; k.Bpad = d->b_pad;
+  k.sa = d->stride_a; k.sb = d->stride_b; k.sr = d->stride_r; k.ss = d->stride_s;
+  k.flip = d->flip; k.col_c = d->col_c;
+}
+
+GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, gdn_stream stream) {
+  if (!d || !w || !out || d->a_pad < d->a || d->b_pad < d->b) return fail(GDN_INVALID_DESC, "gdn_pack_weights: bad arguments");
+  PackK k;
+  fill_pack(d, k);
+  const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.Apad * k.Bpad;
+  pack_weights_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
+  GDN_LAUNCH_CHECK("pack_weights_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* grad, int accumulate, gdn_stream stream) {
+  if (!d || !dw || !grad) return fail(GDN_INVALID_DESC, "gdn_unpack_wgrad: null pointer");
+  PackK k;
+  fill_pack(d, k);
+  const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.A * k.B;
+  unpack_wgrad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(dw, grad, k, accumulate);
+  GDN_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return GDN_OK;
+}

@@ -1,0 +1,505 @@
+// Training loss (fwd + analytic gradient), feature MSE, Eigen depth metrics and fused Adam for sm_100a.
+// All of it is HBM / latency bound single-pass work: vector loads, warp-shuffle + shared-memory reductions,
+// one fp64 atomic per block.  The metric kernel reproduces the reference's fp32 operation order exactly
+// (no FMA contraction, IEEE division) so the delta-threshold pixel COUNTS are bit-exact.
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace gdn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of NV doubles; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum_d(double (&v)[NV], double* smem /* [32*NV] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = warp_sum_d(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) smem[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double t = lane < nw ? smem[lane * NV + i] : 0.0;
+      v[i] = warp_sum_d(t);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------- max |a - b|
+__global__ void absdiff_max_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                   unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(a[i] - b[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    m = lane < (blockDim.x >> 5) ? s[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like their bit patterns
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+struct LossK {
+  const float* out;
+  const float* gt;
+  const float* sparse;
+  long long sparse_stride;
+  const float* rgb;
+  int N, H, W;
+  const float* maxabs;
+  int mode;  // 0 RtoD, 1 DtoD
+  int cy1, cy2, cx1, cx2;
+  float inv_count;
+  double* sums;
+  float* dout;
+  float* dpre;
+  float grad_scale;
+};
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+// Sobel cross-correlation (zero padding) of a single-channel map at (y, x); fx = [[1,0,-1],[2,0,-2],[1,0,-1]],
+// fy = [[1,2,1],[0,0,0],[-1,-2,-1]]  (utils.py:107,115)
+__device__ __forceinline__ void sobel_at(const float* __restrict__ img, int H, int W, int y, int x, float& gx, float& gy) {
+  float v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const int yy = y + a - 1, xx = x + b - 1;
+      v[a][b] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img[(long long)yy * W + xx] : 0.f;
+    }
+  gx = (v[0][0] - v[0][2]) + 2.f * (v[1][0] - v[1][2]) + (v[2][0] - v[2][2]);
+  gy = (v[0][0] + 2.f * v[0][1] + v[0][2]) - (v[2][0] + 2.f * v[2][1] + v[2][2]);
+}
+
+__global__ void loss_kernel(const LossK k) {
+  const long long HW = (long long)k.H * k.W;
+  const long long total = (long long)k.N * HW;
+  const float c = 0.2f * (*k.maxabs);
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % k.W);
+    const int y = (int)((i / k.W) % k.H);
+    const long long n = i / HW;
+    const float* o = k.out + n * HW;
+    const float* g = k.gt + n * HW;
+    const float ov = o[(long long)y * k.W + x];
+    const float d = ov - g[(long long)y * k.W + x];
+    const float a = fabsf(d);
+    // masked BerHu (trainer.py:711-720)
+    float wgt = 1.f;
+    if (k.sparse) {
+      const bool crop = (y >= k.cy1 && y < k.cy2 && x >= k.cx1 && x < k.cx2);
+      if (!crop) wgt = 0.1f;
+      else if (!(k.sparse[n * k.sparse_stride + (long long)y * k.W + x] > -1.f)) wgt = 0.3f;
+    }
+    float val, dv;
+    if (a > c) {
+      val = (d * d + c * c) / (2.f * c);
+      dv = d / c;
+    } else {
+      val = a;
+      dv = sgn(d);
+    }
+    acc[0] += (double)(val * wgt);
+    acc[2] += (double)(d * d);
+    float grad = 3.f * k.inv_count * wgt * dv;
+    if (k.mode == 0) {
+      // edge-aware smoothness (utils.py:139-178, trainer.py:753-754)
+      const float* I = k.rgb + n * 3 * HW;
+      auto wx_at = [&](int yy, int xx) {  // weight of the forward difference starting at (yy, xx), xx < W-1
+        float s = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) s += fabsf(I[ch * HW + (long long)yy * k.W + xx] - I[ch * HW + (long long)yy * k.W + xx + 1]);
+        return expf(-s / 3.f);
+      };
+      auto wy_at = [&](int yy, int xx) {
+        float s = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) s += fabsf(I[ch * HW + (long long)yy * k.W + xx] - I[ch * HW + (long long)(yy + 1) * k.W + xx]);
+        return expf(-s / 3.f);
+      };
+      float sm = 0.f, gs = 0.f;
+      if (x < k.W - 1) {
+        const float gx = ov - o[(long long)y * k.W + x + 1];
+        const float w = wx_at(y, x);
+        sm += fabsf(gx) * w;
+        gs += sgn(gx) * w;
+      }
+      if (x >= 1) {
+        const float gx = o[(long long)y * k.W + x - 1] - ov;
+        gs -= sgn(gx) * wx_at(y, x - 1);
+      }
+      if (y < k.H - 1) {
+        const float gy = ov - o[(long long)(y + 1) * k.W + x];
+        const float w = wy_at(y, x);
+        sm += fabsf(gy) * w;
+        gs += sgn(gy) * w;
+      }
+      if (y >= 1) {
+        const float gy = o[(long long)(y - 1) * k.W + x] - ov;
+        gs -= sgn(gy) * wy_at(y - 1, x);
+      }
+      acc[1] += (double)sm;
+      grad += 0.1f * k.inv_count * gs;
+    } else {
+      // 3 * imgrad_loss (utils.py:105-133, trainer.py:453)
+      float gxo, gyo, gxt, gyt;
+      sobel_at(o, k.H, k.W, y, x, gxo, gyo);
+      sobel_at(g, k.H, k.W, y, x, gxt, gyt);
+      acc[1] += (double)(fabsf(gxo - gxt) + fabsf(gyo - gyt));
+      // adjoint: d/d out(y,x) = sum over neighbours p' of sign(dG(p')) * f[y - y' + 1][x - x' + 1]
+      const float fx[3][3] = {{1.f, 0.f, -1.f}, {2.f, 0.f, -2.f}, {1.f, 0.f, -1.f}};
+      const float fy[3][3] = {{1.f, 2.f, 1.f}, {0.f, 0.f, 0.f}, {-1.f, -2.f, -1.f}};
+      float gs = 0.f;
+#pragma unroll
+      for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll
+        for (int b2 = 0; b2 < 3; b2++) {
+          const int yy = y - (a2 - 1), xx = x - (b2 - 1);  // output position whose window tap (a2,b2) is (y,x)
+          if (yy < 0 || yy >= k.H || xx < 0 || xx >= k.W) continue;
+          float pxo, pyo, pxt, pyt;
+          sobel_at(o, k.H, k.W, yy, xx, pxo, pyo);
+          sobel_at(g, k.H, k.W, yy, xx, pxt, pyt);
+          gs += sgn(pxo - pxt) * fx[a2][b2] + sgn(pyo - pyt) * fy[a2][b2];
+        }
+      grad += 3.f * k.inv_count * gs;
+    }
+    grad *= k.grad_scale;
+    if (k.dout) k.dout[i] = grad;
+    if (k.dpre) k.dpre[i] = grad * (1.f - ov * ov);  // through tanh
+  }
+  __shared__ double sred[32 * 3];
+  block_sum_d<3>(acc, sred);
+  if (threadIdx.x == 0) {
+    atomicAdd(k.sums + 0, acc[0]);
+    atomicAdd(k.sums + 1, acc[1]);
+    atomicAdd(k.sums + 2, acc[2]);
+  }
+}
+
+// ------------------------------------------------------------------------------- sum of squared diffs
+__global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
+                                  double* __restrict__ out) {
+  double acc[1] = {0.0};
+  float part = 0.f;
+  int cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    part += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    if (++cnt == 64) {
+      acc[0] += (double)part;
+      part = 0.f;
+      cnt = 0;
+    }
+  }
+  acc[0] += (double)part;
+  __shared__ double sred[32];
+  block_sum_d<1>(acc, sred);
+  if (threadIdx.x == 0) atomicAdd(out, acc[0]);
+}
+
+// ---------------------------------------------------------------------------------------- Eigen metrics
+// One block per image.  Arithmetic follows calculate_error.py:32-101 operation by operation in fp32.
+struct MetricK {
+  const float* gt_np;  // [B][H][W] sparse / raw ground truth in [-1,1]
+  const float* gt;     // [B][H][W] dense ground truth
+  const float* pred;   // [B][H][W]
+  int B, H, W;
+  int crop, cy1, cy2, cx1, cx2;
+  double* out;         // [8] += per-image metric / B : abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log
+  long long* counts;   // [B][4] = n_valid, n(<1.25), n(<1.25^2), n(<1.25^3)
+};
+
+__device__ __forceinline__ float norm80(float v, float lo, float hi) {
+  return __fmul_rn(__fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo)), 80.f);
+}
+
+// k-th smallest (0-based) of the valid values via 4-pass radix select on the (non-negative) float bit patterns
+template <bool PRED>
+__device__ float select_kth(const MetricK& m, const float* __restrict__ gtn, const float* __restrict__ g,
+                            const float* __restrict__ p, float gmin, float gmax, float pmin, float pmax, long long kth,
+                            unsigned int* hist /* [256] smem */, unsigned int* s_prefix, long long* s_k) {
+  const int HW = m.H * m.W;
+  unsigned int prefix = 0, mask = 0;
+  long long k = kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int y = i / m.W, x = i - y * m.W;
+      const float g80 = norm80(g[i], gmin, gmax);
+      const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
+      bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
+      if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
+      if (!valid) continue;
+      const float v = PRED ? norm80(p[i], pmin, pmax) : g80;
+      const unsigned int bits = __float_as_uint(v);
+      if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long kk = k;
+      unsigned int b = 0;
+      for (; b < 256; b++) {
+        if (kk < (long long)hist[b]) break;
+        kk -= hist[b];
+      }
+      *s_prefix = prefix | (b << shift);
+      *s_k = kk;
+    }
+    __syncthreads();
+    prefix = *s_prefix;
+    k = *s_k;
+    mask |= (255u << shift);
+    __syncthreads();
+  }
+  return __uint_as_float(prefix);
+}
+
+__global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m) {
+  const int b = blockIdx.x;
+  const int HW = m.H * m.W;
+  const float* gtn = m.gt_np + (long long)b * HW;
+  const float* g = m.gt + (long long)b * HW;
+  const float* p = m.pred + (long long)b * HW;
+  __shared__ float s_f[4][32];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix;
+  __shared__ long long s_k;
+  __shared__ double sred[32 * 9];
+  __shared__ float s_mm[4];
+  // 1. min / max of pred and gt (calculate_error.py:38-39)
+  float gmin = INFINITY, gmax = -INFINITY, pmin = INFINITY, pmax = -INFINITY;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float gv = g[i], pv = p[i];
+    gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
+    pmin = fminf(pmin, pv); pmax = fmaxf(pmax, pv);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+  }
+  if (lane == 0) { s_f[0][warp] = gmin; s_f[1][warp] = gmax; s_f[2][warp] = pmin; s_f[3][warp] = pmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; w++) {
+      s_f[0][0] = fminf(s_f[0][0], s_f[0][w]); s_f[1][0] = fmaxf(s_f[1][0], s_f[1][w]);
+      s_f[2][0] = fminf(s_f[2][0], s_f[2][w]); s_f[3][0] = fmaxf(s_f[3][0], s_f[3][w]);
+    }
+    s_mm[0] = s_f[0][0]; s_mm[1] = s_f[1][0]; s_mm[2] = s_f[2][0]; s_mm[3] = s_f[3][0];
+  }
+  __syncthreads();
+  gmin = s_mm[0]; gmax = s_mm[1]; pmin = s_mm[2]; pmax = s_mm[3];
+  // 2. number of valid pixels
+  double cnt[1] = {0.0};
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int y = i / m.W, x = i - y * m.W;
+    const float g80 = norm80(g[i], gmin, gmax);
+    const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
+    bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
+    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
+    if (valid) cnt[0] += 1.0;
+  }
+  block_sum_d<1>(cnt, sred);
+  __shared__ long long s_n;
+  if (threadIdx.x == 0) s_n = (long long)cnt[0];
+  __syncthreads();
+  const long long nvalid = s_n;
+  if (nvalid == 0) {
+    if (threadIdx.x == 0 && m.counts) { for (int j = 0; j < 4; j++) m.counts[b * 4 + j] = 0; }
+    return;  // the reference would produce NaNs here; callers treat n_valid == 0 as "no measurement"
+  }
+  // 3. lower medians (torch.median), calculate_error.py:86
+  const long long kth = (nvalid - 1) / 2;
+  const float med_g = select_kth<false>(m, gtn, g, p, gmin, gmax, pmin, pmax, kth, hist, &s_prefix, &s_k);
+  const float med_p = select_kth<true>(m, gtn, g, p, gmin, gmax, pmin, pmax, kth, hist, &s_prefix, &s_k);
+  // 4. metrics
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int y = i / m.W, x = i - y * m.W;
+    const float g80 = norm80(g[i], gmin, gmax);
+    const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
+    bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
+    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
+    if (!valid) continue;
+    float vp = norm80(p[i], pmin, pmax);
+    vp = __fdiv_rn(__fmul_rn(vp, med_g), med_p);
+    vp = fminf(fmaxf(vp, 1.f), 80.f);
+    const float vg = g80;
+    const float thr = fmaxf(__fdiv_rn(vg, vp), __fdiv_rn(vp, vg));
+    const float d = __fsub_rn(vg, vp);
+    acc[0] += (double)fabsf(d);
+    acc[1] += (double)__fdiv_rn(fabsf(d), vg);
+    acc[2] += (double)__fdiv_rn(__fmul_rn(d, d), vg);
+    acc[3] += (thr < 1.25f) ? 1.0 : 0.0;
+    acc[4] += (thr < 1.5625f) ? 1.0 : 0.0;
+    acc[5] += (thr < 1.953125f) ? 1.0 : 0.0;
+    acc[6] += (double)__fmul_rn(d, d);
+    const float ld = __fsub_rn(logf(vg), logf(vp));
+    acc[7] += (double)__fmul_rn(ld, ld);
+  }
+  block_sum_d<9>(acc, sred);
+  if (threadIdx.x == 0) {
+    const double n = (double)nvalid, invB = 1.0 / (double)m.B;
+    atomicAdd(m.out + 0, acc[0] / n * invB);
+    atomicAdd(m.out + 1, acc[1] / n * invB);
+    atomicAdd(m.out + 2, acc[2] / n * invB);
+    atomicAdd(m.out + 3, (double)((float)acc[3] / (float)nvalid) * invB);
+    atomicAdd(m.out + 4, (double)((float)acc[4] / (float)nvalid) * invB);
+    atomicAdd(m.out + 5, (double)((float)acc[5] / (float)nvalid) * invB);
+    atomicAdd(m.out + 6, sqrt(acc[6] / n) * invB);
+    atomicAdd(m.out + 7, sqrt(acc[7] / n) * invB);
+    if (m.counts) {
+      m.counts[b * 4 + 0] = nvalid;
+      m.counts[b * 4 + 1] = (long long)acc[3];
+      m.counts[b * 4 + 2] = (long long)acc[4];
+      m.counts[b * 4 + 3] = (long long)acc[5];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam semantics with coupled L2 weight decay (GDN_main.py:157,173):
+//   g += wd*p ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
+                            float eps, float wd, float grad_scale) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = reinterpret_cast<float*>(&pp);
+    const float* G = reinterpret_cast<const float*>(&gg);
+    float* M = reinterpret_cast<float*>(&mm);
+    float* V = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float gr = G[j] * grad_scale + wd * P[j];
+      M[j] = b1 * M[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[j]) * inv_sqrt_bc2 + eps;
+      P[j] -= step_size * (M[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * grad_scale + wd * p[i];
+    const float mn = b1 * m[i] + (1.f - b1) * gr;
+    const float vn = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mn;
+    v[i] = vn;
+    p[i] -= step_size * (mn / (sqrtf(vn) * inv_sqrt_bc2 + eps));
+  }
+}
+
+}  // namespace gdn
+
+using namespace gdn;
+#define GDN_API extern "C" __attribute__((visibility("default")))
+
+static int lm_grid(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+GDN_API int gdn_absdiff_max(const float* a, const float* b, int64_t n, float* out_max, gdn_stream stream) {
+  if (!a || !b || !out_max) return fail(GDN_INVALID_DESC, "gdn_absdiff_max: null pointer");
+  absdiff_max_kernel<<<lm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, reinterpret_cast<unsigned int*>(out_max));
+  GDN_LAUNCH_CHECK("absdiff_max_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_loss(const gdn_loss_desc* d, gdn_stream stream) {
+  if (!d || !d->out || !d->gt || !d->maxabs || !d->sums) return fail(GDN_INVALID_DESC, "gdn_loss: null pointer");
+  if (d->mode == 0 && !d->rgb) return fail(GDN_INVALID_DESC, "gdn_loss: RtoD mode needs the rgb input");
+  LossK k{};
+  k.out = d->out; k.gt = d->gt; k.sparse = d->sparse; k.sparse_stride = d->sparse_stride; k.rgb = d->rgb;
+  k.N = d->n; k.H = d->h; k.W = d->w;
+  k.maxabs = d->maxabs;
+  k.mode = d->mode;
+  // Garg ECCV16 crop of the training loss (trainer.py:644-645)
+  k.cy1 = (int)(0.40810811 * d->h); k.cy2 = (int)(0.99189189 * d->h);
+  k.cx1 = (int)(0.03594771 * d->w); k.cx2 = (int)(0.96405229 * d->w);
+  k.inv_count = 1.0f / (float)((long long)d->n * d->h * d->w);
+  k.sums = d->sums; k.dout = d->dout; k.dpre = d->dpre;
+  k.grad_scale = d->grad_scale;
+  loss_kernel<<<lm_grid((long long)d->n * d->h * d->w, 256), 256, 0, (cudaStream_t)stream>>>(k);
+  GDN_LAUNCH_CHECK("loss_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* out, gdn_stream stream) {
+  if (!a || !b || !out || (n & 3)) return fail(GDN_INVALID_DESC, "gdn_sqdiff_sum: bad arguments (n must be a multiple of 4)");
+  sqdiff_sum_kernel<<<lm_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, out);
+  GDN_LAUNCH_CHECK("sqdiff_sum_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
+                              double* out8, int64_t* counts, gdn_stream stream) {
+  if (!gt_np || !gt || !pred || !out8 || b < 1) return fail(GDN_INVALID_DESC, "gdn_eigen_metrics: bad arguments");
+  MetricK m{};
+  m.gt_np = gt_np; m.gt = gt; m.pred = pred;
+  m.B = b; m.H = h; m.W = w; m.crop = crop;
+  // crop used by Godard CVPR17 (calculate_error.py:28-29)
+  m.cy1 = (int)(0.3324324 * h); m.cy2 = (int)(0.91351351 * h);
+  m.cx1 = (int)(0.0359477 * w); m.cx2 = (int)(0.96405229 * w);
+  m.out = out8;
+  m.counts = reinterpret_cast<long long*>(counts);
+  eigen_metrics_kernel<<<b, 1024, 0, (cudaStream_t)stream>>>(m);
+  GDN_LAUNCH_CHECK("eigen_metrics_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float grad_scale, gdn_stream stream) {
+  if (!p || !g || !m || !v || n < 0 || step < 1) return fail(GDN_INVALID_DESC, "gdn_adam_step: bad arguments");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(GDN_INVALID_DESC, "gdn_adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return GDN_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_size, inv_sqrt_bc2, beta1,
+                                                                       beta2, eps, weight_decay, grad_scale);
+  GDN_LAUNCH_CHECK("adam_kernel");
+  return GDN_OK;
+}

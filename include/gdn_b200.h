@@ -88,6 +88,128 @@ typedef struct {
 
 int gdn_conv2d_wgrad(const gdn_wgrad_desc* d, gdn_stream stream);
 
+/* ---- HBM-bound helpers (NHWC; bf16 activations, fp32 residual / gradient streams) ---------------------- */
+
+/* thin-channel lowering: src fp32 planar [n][c][h][w] (c <= 4) -> dst bf16 [n*h*w][kpad],
+ * column k = (r*kw + s)*c + ch holds src[n][ch][y + r - pad][x + s - pad] (reflection or zero padding). */
+int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, int kh, int kw, int pad, int reflect,
+               int kpad, gdn_stream stream);
+
+/* batch statistics -> per-channel scale = gamma*rstd, shift = beta - mean*scale; saves mean / rstd for backward;
+ * updates running stats (momentum, unbiased variance) when running_mean != NULL. */
+int gdn_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* rstd, int c, gdn_stream stream);
+/* eval mode: scale = gamma / sqrt(running_var + eps), bias = beta - running_mean*scale */
+int gdn_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, float* scale,
+                float* bias, int c, gdn_stream stream);
+
+/* y = [ReLU](src*scale + shift) [+ resid];  out_f32 <- y ;  out_bf16 <- pad/upsample/dilate(y)
+ * out_bf16 is [n][OH + 2*pad][OW + 2*pad][c] with OH = 2h when up or dilate; reflect fills the border by
+ * reflection (otherwise the border is left untouched); up: 1 = bilinear x2 align_corners=False, 2 = True;
+ * dilate: y at even positions, zeros elsewhere. */
+typedef struct {
+  const void* src_bf16;
+  const float* src_f32;
+  const float* scale;
+  const float* shift;
+  const float* resid;
+  int32_t relu;
+  int32_t n, h, w, c;
+  float* out_f32;
+  void* out_bf16;
+  int32_t pad, reflect, up, dilate;
+} gdn_act_fwd_desc;
+int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream);
+
+/* BatchNorm(+ReLU) backward.  reduce: sum_g[c] += sum g, sum_gx[c] += sum g*xhat with g = dact*[bn(raw) > 0];
+ * apply (gdn_act_backward): dy = scale*(g - sum_g/n - xhat*sum_gx/n) as bf16 (optionally zero-dilated x2),
+ * dgamma += sum_gx, dbeta += sum_g. */
+typedef struct {
+  const float* dact;
+  const void* raw;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  int32_t relu;
+  int32_t n, h, w, c;
+  double* sum_g;
+  double* sum_gx;
+  void* dy;
+  int32_t dilate;
+  float* dgamma;
+  float* dbeta;
+} gdn_bn_bwd_desc;
+int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream);
+int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream);
+
+/* adjoint of the input transform of a conv: dpad is the fp32 gradient w.r.t. the conv's (padded / upsampled /
+ * dilated) input buffer [n][OH + 2*pad][OW + 2*pad][ctot]; channels [c_off, c_off + c) are folded back onto the
+ * source activation gradient dact [n][h][w][c] (+= when accumulate). */
+typedef struct {
+  const float* dpad;
+  int32_t ctot, c_off;
+  int32_t n, h, w, c;
+  int32_t pad, reflect, up, dilate;
+  float* dact;
+  int32_t accumulate;
+} gdn_fold_desc;
+int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream);
+
+/* fp32 parameter tensor <-> packed operand layout.  packed[t][ai][bi] = w[ai*stride_a + bi*stride_b + r*stride_r +
+ * s*stride_s] (t = r*kw + s, taps flipped when flip), zero padded to a_pad x b_pad, optionally scaled per a.
+ * col_c > 0: im2col'd layer, packed[0][ai][(r*kw + s)*col_c + ch] with stride_b the channel stride.
+ * gdn_unpack_wgrad scatters the wgrad result dw[t][bi][ai] back to the parameter-gradient layout. */
+typedef struct {
+  int32_t kh, kw, a, b, a_pad, b_pad;
+  int64_t stride_a, stride_b, stride_r, stride_s;
+  int32_t flip, col_c;
+} gdn_pack_desc;
+int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, gdn_stream stream);
+int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* grad, int accumulate, gdn_stream stream);
+
+/* ---- training loss, metrics, optimizer ------------------------------------------------------------------ */
+
+/* out_max[0] = max(out_max[0], max_i |a[i] - b[i]|)  (caller zeroes; non-negative float compared as bits).
+ * Replaces c = 0.2*max|diff| of trainer.py:714 (the 0.2 is applied by gdn_loss). */
+int gdn_absdiff_max(const float* a, const float* b, int64_t n, float* out_max, gdn_stream stream);
+
+/* Fused training loss, forward sums + analytic gradient w.r.t. the network output (trainer.py:705-757 RtoD,
+ * :433-456 DtoD).  sums[0] += sum w*BerHu(d), sums[1] += sum of the second term (mode 0: |gx|wx + |gy|wy edge-aware
+ * smoothness; mode 1: |Sobel_x diff| + |Sobel_y diff|), sums[2] += sum d^2.  The loss value is
+ *   mode 0: 3*sums[0]/P + 0.1*sums[1]/P (+ latent)      mode 1: 3*sums[0]/P + 3*sums[1]/P,   P = n*h*w.
+ * dout / dpre (optional) receive grad_scale * dL/d(out) and the same chained through tanh (x (1 - out^2)). */
+typedef struct {
+  const float* out;
+  const float* gt;
+  const float* sparse;      /* channel 0 of the sparse depth (validity = value > -1), or NULL: no crop/validity weights */
+  int64_t sparse_stride;    /* floats between consecutive images of `sparse` */
+  const float* rgb;         /* [n][3][h][w] planar, mode 0 only */
+  int32_t n, h, w;
+  const float* maxabs;      /* device scalar from gdn_absdiff_max (all-reduced MAX by the caller when sharded) */
+  int32_t mode;
+  double* sums;             /* [3], caller zeroes */
+  float* dout;
+  float* dpre;
+  float grad_scale;
+} gdn_loss_desc;
+int gdn_loss(const gdn_loss_desc* d, gdn_stream stream);
+
+/* out[0] += sum_i (a[i] - b[i])^2   (feature MSE of the guidance loss, trainer.py:726-733); n % 4 == 0 */
+int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* out, gdn_stream stream);
+
+/* calculate_error.compute_errors (calculate_error.py:10-103), one CTA per image, exact lower medians by radix
+ * select.  out8 += [abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log] averaged over the b images (caller
+ * zeroes); counts[b][4] = (n_valid, n(thr<1.25), n(thr<1.25^2), n(thr<1.25^3)) may be NULL. */
+int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
+                      double* out8, int64_t* counts, gdn_stream stream);
+
+/* Fused Adam with coupled L2 decay over flat fp32 buffers (torch.optim.Adam semantics); step is 1-based;
+ * the gradient is multiplied by grad_scale first. */
+int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, gdn_stream stream);
+
 const char* gdn_last_error(void);
 int gdn_version(void);
 int gdn_sm_count(void);
