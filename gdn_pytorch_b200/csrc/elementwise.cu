@@ -441,7 +441,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     if (a < k.A) {
       if (k.col_c) {
         const int c = b % k.col_c, tt = b / k.col_c;
-        if (tt < k.kh * k.kw) v = w[a * k.sa + c * k.sb + (tt / k.kw) * k.sr + (tt % k.kw) * k.ss];
+        if (tt < k.kh * k.kw) {
+          int r = tt / k.kw, s2 = tt % k.kw;
+          if (k.flip) { r = k.kh - 1 - r; s2 = k.kw - 1 - s2; }
+          v = w[a * k.sa + c * k.sb + r * k.sr + s2 * k.ss];
+        }
       } else if (b < k.B) {
         int r = t / k.kw, s = t % k.kw;
         if (k.flip) { r = k.kh - 1 - r; s = k.kw - 1 - s; }
@@ -465,7 +469,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
     if (k.col_c) {
       const int c = b % k.col_c, tt = b / k.col_c;
       if (tt >= k.kh * k.kw) continue;
-      widx = a * k.sa + c * k.sb + (tt / k.kw) * k.sr + (tt % k.kw) * k.ss;
+      int r = tt / k.kw, s2 = tt % k.kw;
+      if (k.flip) { r = k.kh - 1 - r; s2 = k.kw - 1 - s2; }
+      widx = a * k.sa + c * k.sb + r * k.sr + s2 * k.ss;
     } else {
       int r = t / k.kw, s = t % k.kw;
       if (k.flip) { r = k.kh - 1 - r; s = k.kw - 1 - s; }

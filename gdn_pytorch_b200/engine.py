@@ -1,0 +1,705 @@
+"""Execution engine: turns a layer graph (graph.py) into a static list of sm_100a kernel launches.
+
+Data layout in HBM (per engine instance, all buffers allocated once):
+  * activations: NHWC bf16, one buffer per (tensor, variant) where the variant is what the consuming conv needs as
+    its TMA source: plain / reflection border of P pixels / x2 bilinear upsample (+ border) / zero-dilated x2.
+    Zero padding is never materialised -- TMA out-of-bounds fill supplies it.
+  * residual stream: fp32 NHWC copy of every tensor that feeds a residual add, is returned to the caller, or
+    feeds the guidance loss (keeps the identity path out of bf16, see DESIGN.md "Tolerances").
+  * training only: bf16 raw conv outputs (pre-BN) + per-channel fp64 statistics, fp32 activation gradients.
+  * weights: bf16 [tap][cout][cin] packs for forward and (flipped / transposed) for the input gradient, refreshed
+    from the fp32 master parameters; eval mode folds BatchNorm into the pack and a bias.
+
+Reference call sites replaced: every nn.Conv2d / ConvTranspose2d / BatchNorm2d / ReLU / ReflectionPad2d /
+F.interpolate / torch.cat in /root/reference/src/AE_model_unet.py (see graph.py) and their autograd.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import Act, ConvDesc, WgradDesc
+from .graph import Graph, Unit
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class ActFwdDesc(C.Structure):
+    _fields_ = [("src_bf16", C.c_void_p), ("src_f32", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("resid", C.c_void_p), ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("pad", C.c_int32),
+                ("reflect", C.c_int32), ("up", C.c_int32), ("dilate", C.c_int32)]
+
+
+class BnBwdDesc(C.Structure):
+    _fields_ = [("dact", C.c_void_p), ("raw", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("c", C.c_int32), ("sum_g", C.c_void_p), ("sum_gx", C.c_void_p), ("dy", C.c_void_p),
+                ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
+class FoldDesc(C.Structure):
+    _fields_ = [("dpad", C.c_void_p), ("ctot", C.c_int32), ("c_off", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("c", C.c_int32), ("pad", C.c_int32), ("reflect", C.c_int32), ("up", C.c_int32),
+                ("dilate", C.c_int32), ("dact", C.c_void_p), ("accumulate", C.c_int32)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("a_pad", C.c_int32),
+                ("b_pad", C.c_int32), ("stride_a", C.c_int64), ("stride_b", C.c_int64), ("stride_r", C.c_int64),
+                ("stride_s", C.c_int64), ("flip", C.c_int32), ("col_c", C.c_int32)]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class _U:
+    """per-unit compiled state"""
+    pass
+
+
+class Engine:
+    def __init__(self, graph: Graph, params: dict, N: int, H: int, W: int, train: bool, backward: bool = False,
+                 want=(), stop_after: str = None, device=None, input_grad: bool = False):
+        """params: state_dict-like mapping (no 'module.' prefix) to the module's OWN cuda fp32 tensors
+        (parameters are read in place, BN running statistics are updated in place in train mode).
+        want: tensor names whose fp32 NHWC value must be available after forward()."""
+        if H % 16 or W % 16:
+            raise ValueError("gdn_b200: height and width must be multiples of 16 (got %dx%d), like the reference "
+                             "networks themselves (SURVEY.md 0.4)" % (H, W))
+        self.L = _lib.lib()
+        self.g, self.P, self.N, self.H, self.W = graph, params, N, H, W
+        self.train, self.do_bwd = train, backward
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.want = set(want)
+        units = []
+        for u in graph.units:
+            units.append(u)
+            if stop_after is not None and u.out == stop_after:
+                break
+        self.units = units
+        self.thin_in = graph.cin < 64          # thin inputs go through im2col; wide ones (stand-alone blocks) are tensors
+        self._infer_shapes()
+        self._plan_tensors()
+        self._alloc()
+        self._build_forward()
+        if backward:
+            self._build_backward()
+        self._wversion = None
+
+    # ------------------------------------------------------------------ shapes
+    def _infer_shapes(self):
+        self.shape = {"in": (self.g.cin, self.H, self.W)}
+        self.producer = {}
+        for u in self.units:
+            c0, h, w = self.shape[u.srcs[0]]
+            if u.up:
+                h, w = 2 * h, 2 * w
+            if u.transposed:
+                ho = (h - 1) * u.stride - 2 * u.pad + u.k
+                wo = (w - 1) * u.stride - 2 * u.pad + u.k
+            else:
+                ho = (h + 2 * u.pad - u.k) // u.stride + 1
+                wo = (w + 2 * u.pad - u.k) // u.stride + 1
+            ctot = sum(self.shape[s][0] for s in u.srcs)
+            assert ctot == u.cin, (u.conv, ctot, u.cin)
+            self.shape[u.out] = (u.cout, ho, wo)
+            self.producer[u.out] = u
+
+    @staticmethod
+    def _variant(u: Unit):
+        """(up, border, reflect, dilate) of the bf16 buffer unit u reads"""
+        dil = 1 if (u.transposed and u.stride == 2) else 0
+        return (u.up, u.pad if u.reflect else 0, 1 if u.reflect else 0, dil)
+
+    def _plan_tensors(self):
+        self.variants = {t: [] for t in self.shape}
+        self.need_f32 = {t: (t in self.want) for t in self.shape}
+        self.consumers = {t: [] for t in self.shape}
+        for u in self.units:
+            for s in u.srcs:
+                self.consumers[s].append(u)
+                if s == "in" and self.thin_in:
+                    continue
+                v = self._variant(u)
+                if v not in self.variants[s]:
+                    self.variants[s].append(v)
+            if u.resid:
+                self.need_f32[u.resid] = True
+        if not self.thin_in:
+            self.need_f32["in"] = True
+        for t, vs in self.variants.items():
+            if t == "in":
+                continue
+            # eval epilogues write plain / reflected borders directly; everything else is derived from the fp32 copy
+            if not self.train:
+                direct = [v for v in vs if not v[0] and not v[3]]
+                if len(direct) != len(vs) or len(direct) > 1:
+                    self.need_f32[t] = True
+        # network heads have no bf16 consumers; their value is the fp32 output
+        for u in self.units:
+            if u.tanh:
+                self.need_f32[u.out] = True
+
+    # ------------------------------------------------------------------ buffers
+    def _buf_dims(self, t, v):
+        c, h, w = self.shape[t]
+        up, pad, refl, dil = v
+        s = 2 if (up or dil) else 1
+        return (self.N, h * s + 2 * pad, w * s + 2 * pad, c)
+
+    def _alloc(self):
+        dev = self.dev
+        self.act = {}    # (tensor, variant) -> bf16 buffer
+        self.f32 = {}    # tensor -> fp32 NHWC
+        nbytes = 0
+        for t, vs in self.variants.items():
+            if t == "in" and self.thin_in:
+                continue
+            for v in vs:
+                self.act[(t, v)] = torch.empty(self._buf_dims(t, v), dtype=torch.bfloat16, device=dev)
+                nbytes += self.act[(t, v)].numel() * 2
+            if self.need_f32[t]:
+                c, h, w = self.shape[t]
+                self.f32[t] = torch.empty((self.N, h, w, c), dtype=torch.float32, device=dev)
+                nbytes += self.f32[t].numel() * 4
+        self.activation_bytes = nbytes
+
+    def _act_struct(self, t, v):
+        buf = self.act[(t, v)]
+        n, hp, wp, c = buf.shape
+        pad = v[1]
+        return Act(buf.data_ptr(), n, hp - 2 * pad, wp - 2 * pad, c, pad)
+
+    # ------------------------------------------------------------------ helpers to emit calls
+    def _call(self, fn, desc, what):
+        L = self.L
+
+        def run(s, fn=fn, desc=desc, what=what):
+            rc = fn(C.byref(desc), s)
+            if rc:
+                _lib.check(rc, what)
+        return run
+
+    def _pack_call(self, pd, wt, scale, out, what, w_off=0):
+        L = self.L
+        wptr = wt.data_ptr() + 4 * w_off
+
+        def run(s):
+            rc = L.gdn_pack_weights(C.byref(pd), C.c_void_p(wptr), C.c_void_p(_ptr(scale)), C.c_void_p(out.data_ptr()), s)
+            if rc:
+                _lib.check(rc, what)
+        return run
+
+    # ------------------------------------------------------------------ forward plan
+    def _geom(self, u: Unit):
+        """conv geometry as executed: (k, stride_exec, off, out_h, out_w, flip)"""
+        c, ho, wo = self.shape[u.out]
+        if u.transposed:
+            # ConvTranspose2d == stride-1 conv with the flipped kernel over the (zero-dilated when stride 2) input
+            return u.k, 1, -(u.k - 1 - u.pad), ho, wo, 1
+        return u.k, u.stride, -u.pad, ho, wo, 0
+
+    def _build_forward(self):
+        L, N, dev = self.L, self.N, self.dev
+        self.fwd = []          # list of callables(stream)
+        self.pack_ops = []     # weight (re)packing, run when parameters changed
+        self.cu = {}
+        self.launches_fwd = 0
+        P = self.P
+        if not self.thin_in:
+            c_in, h_in, w_in = self.shape["in"]
+            self.fwd.append(lambda s: self.f32["in"].copy_(self._x.permute(0, 2, 3, 1)))
+            for v in self.variants["in"]:
+                a = ActFwdDesc()
+                a.src_f32 = self.f32["in"].data_ptr()
+                a.n, a.h, a.w, a.c = N, h_in, w_in, c_in
+                a.out_bf16 = self.act[("in", v)].data_ptr()
+                a.up, a.pad, a.reflect, a.dilate = v
+                self.fwd.append(self._call(L.gdn_act_forward, a, "input variant"))
+                self.launches_fwd += 1
+        for u in self.units:
+            cu = _U()
+            self.cu[u.conv] = cu
+            cu.u = u
+            k, stride, off, ho, wo, flip = self._geom(u)
+            cu.k, cu.stride, cu.off, cu.ho, cu.wo = k, stride, off, ho, wo
+            wt = P[u.conv + ".weight"]
+            cout_pad = 16 if u.cout < 16 else u.cout
+            cu.cout_pad = cout_pad
+            thin = u.cin < 64
+            cu.thin = thin
+            kk = k * k
+            # ---------------- weights (forward pack)
+            if thin:
+                kpad = _round_up(kk * u.cin, 64)
+                cu.kpad = kpad
+                cu.wf = torch.empty((1, cout_pad, kpad), dtype=torch.bfloat16, device=dev)
+                pd = PackDesc(k, k, u.cout, kpad, cout_pad, kpad, u.cin * kk, kk, k, 1, 0, u.cin)
+                assert not u.transposed
+            else:
+                cu.wf = torch.empty((kk, cout_pad, u.cin), dtype=torch.bfloat16, device=dev)
+                if u.transposed:
+                    pd = PackDesc(k, k, u.cout, u.cin, cout_pad, u.cin, kk, u.cout * kk, k, 1, 1, 0)
+                else:
+                    pd = PackDesc(k, k, u.cout, u.cin, cout_pad, u.cin, u.cin * kk, kk, k, 1, 0, 0)
+            cu.pd_fwd = pd
+            bn_eval = (u.bn is not None) and not self.train
+            if bn_eval:
+                cu.fold_scale = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                cu.fold_bias = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                g_, b_ = P[u.bn + ".weight"], P[u.bn + ".bias"]
+                rm, rv = P[u.bn + ".running_mean"], P[u.bn + ".running_var"]
+
+                def fold(s, g_=g_, b_=b_, rm=rm, rv=rv, cu=cu, c=u.cout):
+                    rc = L.gdn_bn_fold(C.c_void_p(g_.data_ptr()), C.c_void_p(b_.data_ptr()), C.c_void_p(rm.data_ptr()),
+                                       C.c_void_p(rv.data_ptr()), C.c_float(BN_EPS), C.c_void_p(cu.fold_scale.data_ptr()),
+                                       C.c_void_p(cu.fold_bias.data_ptr()), c, s)
+                    if rc:
+                        _lib.check(rc, "bn_fold")
+                self.pack_ops.append(fold)
+                self.pack_ops.append(self._pack_call(pd, wt, cu.fold_scale, cu.wf, "pack " + u.conv))
+            else:
+                self.pack_ops.append(self._pack_call(pd, wt, None, cu.wf, "pack " + u.conv))
+
+            # ---------------- input operand(s)
+            d = ConvDesc()
+            if thin:
+                src = u.srcs[0]
+                assert len(u.srcs) == 1 and not u.up and stride == 1
+                c_in, h_in, w_in = self.shape[src]
+                cu.col = torch.empty((N, h_in, w_in, cu.kpad), dtype=torch.bfloat16, device=dev)
+                cu.col_src = src
+
+                def im2col(s, cu=cu, u=u, h_in=h_in, w_in=w_in, k=k):
+                    x = self._thin_input(cu.col_src)
+                    rc = L.gdn_im2col(C.c_void_p(x.data_ptr()), C.c_void_p(cu.col.data_ptr()), N, u.cin, h_in, w_in, k, k,
+                                      u.pad, 1 if u.reflect else 0, cu.kpad, s)
+                    if rc:
+                        _lib.check(rc, "im2col " + u.conv)
+                self.fwd.append(im2col)
+                d.src0 = Act(cu.col.data_ptr(), N, h_in, w_in, cu.kpad, 0)
+                d.kh = d.kw = 1
+                d.stride = 1
+                d.off_y = d.off_x = 0
+            else:
+                v = self._variant(u)
+                d.src0 = self._act_struct(u.srcs[0], v)
+                if len(u.srcs) == 2:
+                    d.src1 = self._act_struct(u.srcs[1], v)
+                d.kh = d.kw = k
+                d.stride = stride
+                d.off_y = d.off_x = off
+            d.weights = cu.wf.data_ptr()
+            d.out_h, d.out_w = ho, wo
+            d.cout, d.cout_pad = u.cout, cout_pad
+            d.algo = 0
+            d.dst_h, d.dst_w = ho, wo
+            d.dst_sy = d.dst_sx = 1
+            cu.conv_desc = d
+            out_vs = self.variants[u.out]
+            if self.train and u.bn is not None:
+                # raw conv output + statistics, then BatchNorm apply into every variant the consumers need
+                cu.raw = torch.empty((N, ho, wo, u.cout), dtype=torch.bfloat16, device=dev)
+                cu.stat = torch.zeros((2, u.cout), dtype=torch.float64, device=dev)
+                cu.scale = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                cu.shift = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                cu.mean = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                cu.rstd = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                d.out_bf16 = Act(cu.raw.data_ptr(), N, ho, wo, u.cout, 0)
+                d.stat_sum = cu.stat[0].data_ptr()
+                d.stat_sqsum = cu.stat[1].data_ptr()
+                self.fwd.append(lambda s, cu=cu: cu.stat.zero_())
+                self.fwd.append(self._call(L.gdn_conv2d, d, "conv " + u.conv))
+                g_, b_ = P[u.bn + ".weight"], P[u.bn + ".bias"]
+                rm, rv = P[u.bn + ".running_mean"], P[u.bn + ".running_var"]
+                cnt = float(N * ho * wo)
+
+                def finalize(s, cu=cu, g_=g_, b_=b_, rm=rm, rv=rv, cnt=cnt, c=u.cout):
+                    rc = L.gdn_bn_finalize(C.c_void_p(cu.stat[0].data_ptr()), C.c_void_p(cu.stat[1].data_ptr()),
+                                           C.c_double(cnt), C.c_void_p(g_.data_ptr()), C.c_void_p(b_.data_ptr()),
+                                           C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), C.c_void_p(rm.data_ptr()),
+                                           C.c_void_p(rv.data_ptr()), C.c_void_p(cu.scale.data_ptr()),
+                                           C.c_void_p(cu.shift.data_ptr()), C.c_void_p(cu.mean.data_ptr()),
+                                           C.c_void_p(cu.rstd.data_ptr()), c, s)
+                    if rc:
+                        _lib.check(rc, "bn_finalize " + u.conv)
+                self.fwd.append(finalize)
+                self.launches_fwd += 2
+                first = True
+                todo = list(out_vs) if out_vs else [None]
+                for v in todo:
+                    a = ActFwdDesc()
+                    a.src_bf16 = cu.raw.data_ptr()
+                    a.scale, a.shift = cu.scale.data_ptr(), cu.shift.data_ptr()
+                    a.resid = _ptr(self.f32.get(u.resid)) if u.resid else None
+                    a.relu = int(u.relu)
+                    a.n, a.h, a.w, a.c = N, ho, wo, u.cout
+                    if first and self.need_f32[u.out]:
+                        a.out_f32 = self.f32[u.out].data_ptr()
+                    if v is not None:
+                        a.out_bf16 = self.act[(u.out, v)].data_ptr()
+                        a.up, a.pad, a.reflect, a.dilate = v
+                    if a.out_f32 or a.out_bf16:
+                        self.fwd.append(self._call(L.gdn_act_forward, a, "act " + u.conv))
+                        self.launches_fwd += 1
+                    first = False
+            else:
+                # eval (BN folded) or no BN: the conv epilogue produces the activation itself
+                if u.bn is not None:
+                    d.bias = cu.fold_bias.data_ptr()
+                d.relu = int(u.relu)
+                d.tanh_out = int(u.tanh)
+                if u.resid:
+                    d.resid = self.f32[u.resid].data_ptr()
+                if self.need_f32[u.out]:
+                    d.out_f32 = self.f32[u.out].data_ptr()
+                direct = [v for v in out_vs if not v[0] and not v[3]]
+                derived = [v for v in out_vs if v[0] or v[3]]
+                if direct:
+                    v = direct[0]
+                    d.out_bf16 = self._act_struct(u.out, v)
+                    d.out_reflect = v[2]
+                self.fwd.append(self._call(L.gdn_conv2d, d, "conv " + u.conv))
+                self.launches_fwd += 1
+                for v in direct[1:] + derived:
+                    a = ActFwdDesc()
+                    a.src_f32 = self.f32[u.out].data_ptr()
+                    a.n, a.h, a.w, a.c = N, ho, wo, u.cout
+                    a.out_bf16 = self.act[(u.out, v)].data_ptr()
+                    a.up, a.pad, a.reflect, a.dilate = v
+                    self.fwd.append(self._call(L.gdn_act_forward, a, "variant " + u.conv))
+                    self.launches_fwd += 1
+                if (direct[1:] or derived) and not self.need_f32[u.out]:
+                    raise AssertionError("variant derivation needs the fp32 copy of " + u.out)
+
+    def _thin_input(self, name):
+        if name == "in":
+            return self._x
+        return self.f32[name]
+
+    # ------------------------------------------------------------------ running
+    def refresh_weights(self, stream=None):
+        s = stream or _lib.stream_ptr()
+        for op in self.pack_ops:
+            op(s)
+        if self.do_bwd:
+            for op in self.pack_ops_bwd:
+                op(s)
+
+    def _param_version(self):
+        return tuple(t._version for t in self.P.values())
+
+    def forward(self, x):
+        """x: fp32 NCHW cuda tensor (N, cin, H, W).  Returns nothing; read results with value()/depth()."""
+        if x.shape != (self.N, self.g.cin, self.H, self.W):
+            raise ValueError("gdn_b200 engine built for %s, got %s" % ((self.N, self.g.cin, self.H, self.W), tuple(x.shape)))
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("gdn_b200: input must be a CUDA fp32 tensor")
+        self._x = x.contiguous()
+        s = _lib.stream_ptr()
+        ver = self._param_version()
+        if ver != self._wversion:
+            self.refresh_weights(s)
+            self._wversion = ver
+        for op in self.fwd:
+            op(s)
+        if self.train:
+            self._wversion = None if self.do_bwd else self._param_version()  # running stats were updated in place
+
+    def value(self, name):
+        """fp32 NHWC buffer of a tensor (valid until the next forward)"""
+        return self.f32[name]
+
+    def value_nchw(self, name):
+        """(N, C, H, W)-shaped view (channels_last strides) of the fp32 buffer"""
+        return self.f32[name].permute(0, 3, 1, 2)
+
+    def depth(self):
+        """network output (N, 1, H, W) fp32 (C == 1, so NHWC and NCHW coincide)"""
+        t = self.units[-1].out
+        return self.f32[t].view(self.N, 1, self.H, self.W)
+
+    # ------------------------------------------------------------------ backward plan
+    def _build_backward(self):
+        L, N, dev, P = self.L, self.N, self.dev, self.P
+        assert self.train
+        self.bwd = []
+        self.pack_ops_bwd = []
+        self.launches_bwd = 0
+        # parameter gradients: one flat fp32 buffer, views per parameter in state_dict order
+        names = [k for k, t in P.items() if t.dtype == torch.float32 and getattr(t, "requires_grad", False)]
+        self.param_names = names
+        total = sum(_round_up(P[k].numel(), 4) for k in names)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = {}
+        o = 0
+        for k in names:
+            n = P[k].numel()
+            self.grad[k] = self.flat_grad[o:o + n].view(P[k].shape)
+            o += _round_up(n, 4)
+        # activation gradients (fp32 NHWC) for every tensor except the input
+        self.dact = {}
+        for t in self.shape:
+            if t == "in" and self.thin_in:
+                continue
+            c, h, w = self.shape[t]
+            self.dact[t] = torch.empty((N, h, w, c), dtype=torch.float32, device=dev)
+        self._dset = {}   # tensor -> bool (runtime: has a gradient been written in this backward pass?)
+        maxdw = 0
+        for u in self.units:
+            cu = self.cu[u.conv]
+            maxdw = max(maxdw, (1 if cu.thin else cu.k * cu.k) * (cu.kpad if cu.thin else u.cin) * max(cu.cout_pad, 64))
+        maxdw = max(maxdw, 128 * 64)
+        self.dw_scratch = torch.zeros(maxdw, dtype=torch.float32, device=dev)
+        self.bn_sums = torch.zeros((2, 512), dtype=torch.float64, device=dev)
+
+        order = []  # static accumulation bookkeeping: which tensors already hold a gradient at each point
+        have = set()
+        have.add(self.units[-1].out)
+
+        def accumulate_flag(t):
+            f = t in have
+            have.add(t)
+            return f
+
+        for u in reversed(self.units):
+            cu = self.cu[u.conv]
+            k, stride, off, ho, wo = cu.k, cu.stride, cu.off, cu.ho, cu.wo
+            kk = k * k
+            wt = P[u.conv + ".weight"]
+            if u.out not in have:
+                continue  # tensor does not influence the loss (e.g. dead branch): no gradient flows
+            g_out = self.dact[u.out]
+            if u.tanh:
+                self._build_head_backward(u, cu, have)
+                continue
+            # ---- residual identity: d(resid) (+)= g_out
+            if u.resid:
+                acc = accumulate_flag(u.resid)
+                a = ActFwdDesc()
+                a.src_f32 = g_out.data_ptr()
+                a.resid = self.dact[u.resid].data_ptr() if acc else None
+                a.n, a.h, a.w, a.c = N, ho, wo, u.cout
+                a.out_f32 = self.dact[u.resid].data_ptr()
+                self.bwd.append(self._call(L.gdn_act_forward, a, "resid-grad " + u.conv))
+                self.launches_bwd += 1
+            # ---- BatchNorm (+ReLU) backward -> dy (bf16)
+            assert u.bn is not None, "training needs BatchNorm on every hidden conv (" + u.conv + ")"
+            cu.dy = torch.empty((N, ho, wo, u.cout), dtype=torch.bfloat16, device=dev)
+            b = BnBwdDesc()
+            b.dact, b.raw = g_out.data_ptr(), cu.raw.data_ptr()
+            b.scale, b.shift, b.mean, b.rstd = (cu.scale.data_ptr(), cu.shift.data_ptr(), cu.mean.data_ptr(),
+                                                cu.rstd.data_ptr())
+            b.relu = int(u.relu)
+            b.n, b.h, b.w, b.c = N, ho, wo, u.cout
+            b.sum_g, b.sum_gx = self.bn_sums[0].data_ptr(), self.bn_sums[1].data_ptr()
+            b.dy = cu.dy.data_ptr()
+            b.dilate = 0
+            b.dgamma = self.grad[u.bn + ".weight"].data_ptr()
+            b.dbeta = self.grad[u.bn + ".bias"].data_ptr()
+            self.bwd.append(lambda s: self.bn_sums.zero_())
+            self.bwd.append(self._call(L.gdn_bn_bwd_reduce, b, "bn_bwd_reduce " + u.conv))
+            self.bwd.append(self._call(L.gdn_act_backward, b, "act_backward " + u.conv))
+            self.launches_bwd += 2
+            need_dgrad = [s for s in u.srcs if not (s == "in" and self.thin_in)]
+            fwd_stride2 = (not u.transposed) and u.stride == 2
+            if fwd_stride2 and need_dgrad:
+                cu.dy_dil = torch.empty((N, 2 * ho, 2 * wo, u.cout), dtype=torch.bfloat16, device=dev)
+                b2 = BnBwdDesc()
+                C.memmove(C.byref(b2), C.byref(b), C.sizeof(b))
+                b2.dy = cu.dy_dil.data_ptr()
+                b2.dilate = 1
+                b2.dgamma = None
+                b2.dbeta = None
+                self.bwd.append(self._call(L.gdn_act_backward, b2, "act_backward(dilated) " + u.conv))
+                self.launches_bwd += 1
+            # ---- weight gradient (same geometry as the forward conv)
+            wd = WgradDesc()
+            fd = cu.conv_desc
+            wd.x0, wd.x1 = fd.src0, fd.src1
+            cpad64 = _round_up(cu.cout_pad, 64)
+            assert cpad64 == u.cout, "hidden convs have >= 64 output channels"
+            wd.dy = Act(cu.dy.data_ptr(), N, ho, wo, u.cout, 0)
+            cin_eff = cu.kpad if cu.thin else u.cin
+            taps_eff = 1 if cu.thin else kk
+            dw = self.dw_scratch[: taps_eff * cin_eff * u.cout]
+            wd.dw = dw.data_ptr()
+            wd.kh, wd.kw, wd.stride = fd.kh, fd.kw, fd.stride
+            wd.off_y, wd.off_x = fd.off_y, fd.off_x
+            wd.out_h, wd.out_w, wd.cout_pad = ho, wo, u.cout
+            self.bwd.append(lambda s, dw=dw: dw.zero_())
+            self.bwd.append(self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv))
+            if cu.thin:
+                up_ = PackDesc(k, k, u.cout, cu.kpad, u.cout, cu.kpad, u.cin * kk, kk, k, 1, 0, u.cin)
+            elif u.transposed:
+                up_ = PackDesc(k, k, u.cout, u.cin, u.cout, u.cin, kk, u.cout * kk, k, 1, 1, 0)
+            else:
+                up_ = PackDesc(k, k, u.cout, u.cin, u.cout, u.cin, u.cin * kk, kk, k, 1, 0, 0)
+            gbuf = self.grad[u.conv + ".weight"]
+
+            def unpack(s, up_=up_, dw=dw, gbuf=gbuf, name=u.conv):
+                rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr()), 1, s)
+                if rc:
+                    _lib.check(rc, "unpack " + name)
+            self.bwd.append(unpack)
+            self.launches_bwd += 2
+            # ---- input gradient(s)
+            c_off = 0
+            for si, s_name in enumerate(u.srcs):
+                cs = self.shape[s_name][0]
+                if s_name == "in" and self.thin_in:
+                    c_off += cs
+                    continue
+                self._build_dgrad(u, cu, s_name, c_off, cs, accumulate_flag(s_name))
+                c_off += cs
+
+    def _build_dgrad(self, u, cu, s_name, c_off, cs, acc):
+        """gradient of unit u w.r.t. source tensor s_name (channels [c_off, c_off+cs) of its input)"""
+        L, N, dev, P = self.L, self.N, self.dev, self.P
+        k, kk = cu.k, cu.k * cu.k
+        wt = P[u.conv + ".weight"]
+        v = self._variant(u)
+        up, pad_phys, refl, dil = v
+        c_s, h_s, w_s = self.shape[s_name]
+        # dgrad weight pack: [tap][a = ci of this source][b = co]
+        wdg = torch.empty((kk, cs, u.cout), dtype=torch.bfloat16, device=dev)
+        if u.transposed:
+            # w is (cin, cout, k, k): dX = conv(dy, w) -- no flip
+            pd = PackDesc(k, k, cs, u.cout, cs, u.cout, u.cout * kk, kk, k, 1, 0, 0)
+            w_off = c_off * u.cout * kk
+        else:
+            pd = PackDesc(k, k, cs, u.cout, cs, u.cout, kk, u.cin * kk, k, 1, 1, 0)
+            w_off = c_off * kk
+        self.pack_ops_bwd.append(self._pack_call(pd, wt, None, wdg, "pack-dgrad " + u.conv, w_off))
+        d = ConvDesc()
+        d.weights = wdg.data_ptr()
+        d.kh = d.kw = k
+        d.cout = d.cout_pad = cs
+        d.algo = 0
+        d.dst_sy = d.dst_sx = 1
+        direct = (not up) and (not refl) and (not dil)
+        if u.transposed and u.stride == 2:
+            # dX[y] = sum_t dy[2y + t - p] w[t]: stride-2 conv over dy, straight onto the source gradient
+            d.src0 = Act(cu.dy.data_ptr(), N, cu.ho, cu.wo, u.cout, 0)
+            d.stride = 2
+            d.off_y = d.off_x = -u.pad
+            d.out_h, d.out_w = h_s, w_s
+            direct = True
+        else:
+            offb = cu.off + pad_phys            # forward offset in buffer coordinates
+            if (not u.transposed) and u.stride == 2:
+                d.src0 = Act(cu.dy_dil.data_ptr(), N, 2 * cu.ho, 2 * cu.wo, u.cout, 0)
+            else:
+                d.src0 = Act(cu.dy.data_ptr(), N, cu.ho, cu.wo, u.cout, 0)
+            d.stride = 1
+            d.off_y = d.off_x = -(k - 1) - offb
+            sc = 2 if (up or dil) else 1
+            d.out_h, d.out_w = h_s * sc + 2 * pad_phys, w_s * sc + 2 * pad_phys
+        d.dst_h, d.dst_w = d.out_h, d.out_w
+        if direct:
+            tgt = self.dact[s_name]
+            d.out_f32 = tgt.data_ptr()
+            d.resid = tgt.data_ptr() if acc else None
+            self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+            self.launches_bwd += 1
+        else:
+            tmp = torch.empty((N, d.out_h, d.out_w, cs), dtype=torch.float32, device=dev)
+            d.out_f32 = tmp.data_ptr()
+            self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+            f = FoldDesc()
+            f.dpad = tmp.data_ptr()
+            f.ctot, f.c_off = cs, 0
+            f.n, f.h, f.w, f.c = N, h_s, w_s, cs
+            f.pad, f.reflect, f.up, f.dilate = pad_phys, refl, up, dil
+            f.dact = self.dact[s_name].data_ptr()
+            f.accumulate = int(acc)
+            self.bwd.append(self._call(L.gdn_fold_grad, f, "fold " + u.conv))
+            self.launches_bwd += 2
+            cu.keep = getattr(cu, "keep", []) + [tmp]
+        cu.keep = getattr(cu, "keep", []) + [wdg]
+
+    def _build_head_backward(self, u, cu, have):
+        """64 -> 1 head (k9, zero pad 4, tanh): the caller supplies dL/d(pre-tanh) as fp32 (N, H, W); it is im2col'd
+        (81 taps -> 128 columns) so that both gradients run as 1x1 problems on the tensor cores."""
+        L, N, dev, P = self.L, self.N, self.dev, self.P
+        k, kk = cu.k, cu.k * cu.k
+        ho, wo = cu.ho, cu.wo
+        src = u.srcs[0]
+        wt = P[u.conv + ".weight"]
+        self.dpre = torch.zeros((N, ho, wo), dtype=torch.float32, device=dev)
+        kp = _round_up(kk, 64)
+        dcol = torch.empty((N, ho, wo, kp), dtype=torch.bfloat16, device=dev)
+        cu.dcol = dcol
+
+        def im2col(s):
+            rc = L.gdn_im2col(C.c_void_p(self.dpre.data_ptr()), C.c_void_p(dcol.data_ptr()), N, 1, ho, wo, k, k, u.pad, 0, kp, s)
+            if rc:
+                _lib.check(rc, "im2col(dpre)")
+        self.bwd.append(im2col)
+        # input gradient: dX[q][c] = sum_t' dcol[q][t'] * Wd[c][t'],  Wd[c][t'] = w[c][flip(t')] (conv) / w[c][t'] (convT)
+        wdg = torch.empty((1, u.cin, kp), dtype=torch.bfloat16, device=dev)
+        pd = PackDesc(k, k, u.cin, kp, u.cin, kp, kk, 0, k, 1, 0 if u.transposed else 1, 1)
+        self.pack_ops_bwd.append(self._pack_call(pd, wt, None, wdg, "pack-dgrad head"))
+        d = ConvDesc()
+        d.src0 = Act(dcol.data_ptr(), N, ho, wo, kp, 0)
+        d.weights = wdg.data_ptr()
+        d.kh = d.kw = 1
+        d.stride = 1
+        d.out_h, d.out_w = ho, wo
+        d.cout = d.cout_pad = u.cin
+        d.dst_h, d.dst_w = ho, wo
+        d.dst_sy = d.dst_sx = 1
+        acc = src in have
+        have.add(src)
+        tgt = self.dact[src]
+        d.out_f32 = tgt.data_ptr()
+        d.resid = tgt.data_ptr() if acc else None
+        self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad head"))
+        # weight gradient: dw[0][c][t'] = sum_q x[q][c] * dcol[q][t']
+        v = self._variant(u)
+        wd = WgradDesc()
+        wd.x0 = self._act_struct(src, v)
+        wd.dy = Act(dcol.data_ptr(), N, ho, wo, kp, 0)
+        dw = self.dw_scratch[: u.cin * kp]
+        wd.dw = dw.data_ptr()
+        wd.kh = wd.kw = 1
+        wd.stride = 1
+        wd.out_h, wd.out_w, wd.cout_pad = ho, wo, kp
+        self.bwd.append(lambda s, dw=dw: dw.zero_())
+        self.bwd.append(self._call(L.gdn_conv2d_wgrad, wd, "wgrad head"))
+        gbuf = self.grad[u.conv + ".weight"]
+        # dw is [ci = c][co = t'] ; parameter is w[0][c][r][s] (conv, taps flipped) or w[c][0][r][s] (convT)
+        if u.transposed:
+            up_ = PackDesc(1, 1, kk, u.cin, kp, u.cin, 1, kk, 0, 0, 0, 0)
+            goff = 0
+        else:
+            up_ = PackDesc(1, 1, kk, u.cin, kp, u.cin, -1, kk, 0, 0, 0, 0)
+            goff = kk - 1
+
+        def unpack(s):
+            rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr() + 4 * goff), 1, s)
+            if rc:
+                _lib.check(rc, "unpack head")
+        self.bwd.append(unpack)
+        self.launches_bwd += 5
+        cu.keep = [wdg]
+
+    def backward(self, dpre=None, dout_nhwc=None):
+        """dpre: dL/d(pre-tanh output), fp32 (N, H, W) -- or None if the loss kernel already wrote self.dpre.
+        dout_nhwc: for graphs without a tanh head (stand-alone blocks), the gradient of the last tensor.
+        Parameter gradients are ACCUMULATED into self.grad[...] (views of self.flat_grad)."""
+        if dpre is not None:
+            self.dpre.copy_(dpre.reshape(self.dpre.shape))
+        if dout_nhwc is not None:
+            self.dact[self.units[-1].out].copy_(dout_nhwc)
+        s = _lib.stream_ptr()
+        for op in self.bwd:
+            op(s)
