@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the GDN hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                      # this implementation
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # reference CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                                  # N ranks, batch-sharded (weak scaling)
+
+Workload (BASELINE.json metric "RtoD train imgs/s @128x416", configs[3]): one RtoD training step per "step" --
+AutoEncoder_2 forward, two frozen AutoEncoder_DtoD guidance passes, masked BerHu + latent MSE + smoothness loss,
+backward, Adam -- batch 20 per GPU, synthetic KITTI-shaped 128x416 inputs, random-init weights (seed 0).
+  value : images/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : images/s through the same public step() with pinned-host inputs copied H2D and the loss read back D2H
+          inside the timed region
+  roofline : the dominant kernel (64->64 k9 implicit-GEMM conv, 34 % of forward FLOPs) timed alone, live
+  cpu_baseline : the oracle port of the reference step timed on this box's host cores on a bounded sample
+`--workload infer` measures BASELINE configs[1] instead (RtoD inference batch 8 + guidance features + Eigen metrics).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+H, W = 128, 416
+GFLOP_RTOD_TRAIN = 1595.2   # per image, canonical: 3 x 414.75 + 2 x 175.48
+GFLOP_RTOD_INFER = 414.75 + 175.48
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(s[i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synth_batch(B, seed):
+    from oracle import synth   # input generators only (shared with the tests); nothing of the oracle is timed here
+    rgb = synth.synth_rgb(B, H, W, seed)
+    dep = synth.synth_depth(B, H, W, seed)
+    spa = synth.synth_sparse(dep, seed)
+    return rgb, dep, spa
+
+
+def build_models(dev):
+    import contextlib, io
+    from gdn_pytorch_b200 import AE_model_unet as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(0)
+        rtod = M.AutoEncoder_2(norm="Batch", input_dim=3, height=H, width=W)
+        torch.manual_seed(1)
+        dtod = M.AutoEncoder_DtoD(norm="Batch", input_dim=1, height=H, width=W)
+    return rtod.to(dev), dtod.to(dev).eval()
+
+
+def time_dominant_conv(dev, B):
+    """64->64 k9 same conv on (B,128,416): the kernel that dominates the step, timed alone with CUDA events"""
+    import ctypes as C
+    from gdn_pytorch_b200 import _lib
+    x = torch.randn((B, H, W, 64), device=dev).to(torch.bfloat16)
+    w = (torch.randn((81, 64, 64), device=dev) * 0.01).to(torch.bfloat16)
+    raw = torch.empty((B, H, W, 64), dtype=torch.float16, device=dev)
+    st = torch.zeros((2, 64), dtype=torch.float64, device=dev)
+    d = _lib.ConvDesc()
+    d.src0 = _lib.Act(x.data_ptr(), B, H, W, 64, 0)
+    d.weights = w.data_ptr()
+    d.kh = d.kw = 9
+    d.stride = 1
+    d.off_y = d.off_x = -4
+    d.out_h, d.out_w, d.cout, d.cout_pad = H, W, 64, 64
+    d.dst_h, d.dst_w, d.dst_sy, d.dst_sx = H, W, 1, 1
+    d.out_bf16 = _lib.Act(raw.data_ptr(), B, H, W, 64, 0)
+    d.out16_is_half = 1
+    d.stat_sum, d.stat_sqsum = st[0].data_ptr(), st[1].data_ptr()
+    L = _lib.lib()
+    for _ in range(3):
+        _lib.check(L.gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        L.gdn_conv2d(C.byref(d), _lib.stream_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * H * W * 64 * 64 * 81
+    return ms, flops
+
+
+def cpu_step_fn(B):
+    """the reference's RtoD training step restated on CPU (oracle port): returns a callable doing one step"""
+    from oracle import model as OM, losses as OL, synth
+    from tests.util import shapes_of
+    sd = synth.synth_state_dict(shapes_of("AutoEncoder_2"), seed=0, bn_random=False)
+    sdd = synth.synth_state_dict(shapes_of("AutoEncoder_DtoD"), seed=1, bn_random=False)
+    pn = [k for k in sd if sd[k].dtype == torch.float32 and not k.endswith(("running_mean", "running_var"))]
+    for k in pn:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in pn], 2e-5, (0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    rgb, dep, spa = synth_batch(B, 0)
+
+    def step():
+        out = OM.autoencoder_2(sd, rgb, istrain=False, train=True, update_running=True)
+        with torch.no_grad():   # the reference runs the WHOLE DtoD network twice (trainer.py:699-703)
+            ft_tar = OM.autoencoder_dtod(sdd, dep, istrain=True)[:4]
+            ft = OM.autoencoder_dtod(sdd, out, istrain=True)[:4]
+        terms = OL.rtod_loss(out, dep, spa, rgb, ft, ft_tar)
+        opt.zero_grad()
+        terms["loss"].backward()
+        opt.step()
+        return float(terms["loss"])
+    return step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 2
+    step = cpu_step_fn(B)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = B / dt
+    line = {
+        "impl": "reference", "metric": "RtoD train imgs/s @128x416", "value": v, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RtoD training step (AutoEncoder_2 + 2 frozen DtoD passes + loss + bwd + Adam), 128x416, "
+                               "CPU sample batch %d per step" % B},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "batch %d per step, fp32 torch CPU ops via the oracle port of the reference step "
+                                   "(/root/reference is not present on the GPU box)" % B},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    from gdn_pytorch_b200.trainer import init_distributed_from_env, RtoDTrainStep
+    from gdn_pytorch_b200 import ops
+    rank, world, dev = init_distributed_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    B = args.batch or (20 if args.workload == "train" else 8)
+    rgb_h, dep_h, spa_h = [t.pin_memory() for t in synth_batch(B, rank)]
+    rgb, dep, spa = rgb_h.to(dev), dep_h.to(dev), spa_h.to(dev)
+    rtod, dtod = build_models(dev)
+    launches = [0]
+
+    if args.workload == "train":
+        stepper = RtoDTrainStep(rtod, dtod, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+
+        def step_dev():
+            return stepper.step(rgb, dep, spa)
+
+        def step_e2e():
+            r = rgb_h.to(dev, non_blocking=True)
+            d = dep_h.to(dev, non_blocking=True)
+            s = spa_h.to(dev, non_blocking=True)
+            return float(stepper.step(r, d, s)["loss"])   # D2H read of the loss
+        h2d = (rgb_h.numel() + dep_h.numel() + spa_h.numel()) * 4
+        d2h = 8
+        gflop_img = GFLOP_RTOD_TRAIN
+        metric = "RtoD train imgs/s @128x416"
+        workload = ("RtoD training step, batch %d per GPU, 128x416 (BASELINE configs[3]): AutoEncoder_2 fwd + 2 frozen "
+                    "DtoD encoder passes + loss + bwd + fused Adam" % B)
+    else:
+        from gdn_pytorch_b200.module_runtime import encoder_features
+        rtod.eval()
+
+        def infer(r, d, s):
+            with torch.no_grad():
+                out = rtod(r, istrain=False)
+                encoder_features(dtod, out)
+                return ops.eigen_metrics_device(s, d, out, crop=True)[0]
+
+        def step_dev():
+            return infer(rgb, dep, spa)
+
+        def step_e2e():
+            r = rgb_h.to(dev, non_blocking=True)
+            d = dep_h.to(dev, non_blocking=True)
+            s = spa_h.to(dev, non_blocking=True)
+            return infer(r, d, s).tolist()
+        h2d = (rgb_h.numel() + dep_h.numel() + spa_h.numel()) * 4
+        d2h = 64
+        gflop_img = GFLOP_RTOD_INFER
+        metric = "RtoD infer imgs/s @128x416"
+        workload = "RtoD inference batch %d + DtoD guidance features + Eigen metrics, 128x416 (BASELINE configs[1])" % B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_dev, args.steps)
+    clocks = sampler.summary() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    ms_step = ms / args.steps
+    value = B * world / (ms_step / 1e3)
+    e2e_v = B * world / (ms_e2e / args.steps / 1e3)
+
+    if rank == 0:
+        burst, sustained, hbm, src = peaks()
+        cms, cfl = time_dominant_conv(dev, B)
+        achieved = cfl / (cms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<64> (64->64 k9 s1, halo-resident)", "achieved": achieved,
+                "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                "peak_source": src + " burst bf16 (kernel timed alone)", "ms_per_launch": cms,
+                "step_tflops": gflop_img * B / ms_step / 1e3 * 1e3 / 1e3,
+                "step_frac_of_sustained": (gflop_img * B / (ms_step / 1e3) / 1e3) / sustained}
+        roof["step_tflops"] = gflop_img * B / (ms_step / 1e3) / 1e3
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline and args.workload == "train":
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cstep = cpu_step_fn(2)
+            cstep()
+            t0 = time.perf_counter()
+            cstep()
+            dt = time.perf_counter() - t0
+            cpu = {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "1 warm-up + 1 timed RtoD training step at batch 2 (fp32 torch CPU ops, oracle port)"}
+        eng = getattr(locals().get("stepper", None), "eng", None)
+        if args.workload == "train":
+            per_step = (eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) +
+                        sum(e.launches_fwd for e in stepper.deng if e is not None) + 2 + 4 + 1)
+        else:
+            per_step = sum(e.launches_fwd for e in rtod.__dict__["_gdn_engines"].values()) + \
+                sum(e.launches_fwd for e in dtod.__dict__["_gdn_engines"].values()) + 1
+        line = {
+            "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "batch_per_gpu": B, "parallelism": "dp%d" % world,
+                       "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": per_step * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
         ("resid", C.c_void_p), ("out_f32", C.c_void_p), ("out_bf16", Act), ("out_reflect", C.c_int32),
         ("dst_h", C.c_int32), ("dst_w", C.c_int32), ("dst_sy", C.c_int32), ("dst_sx", C.c_int32),
         ("dst_oy", C.c_int32), ("dst_ox", C.c_int32),
-        ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p),
+        ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("out16_is_half", C.c_int32),
     ]
 
 

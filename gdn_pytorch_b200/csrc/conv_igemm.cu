@@ -17,6 +17,7 @@
 //   TAPBOX (anything: stride 2, 1x1 on a virtual concat of two sources, tiny maps): one TMA box per (tap, chunk).
 // (tools/probe_umma.cu is the hardware check of the descriptor semantics this relies on.)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -43,7 +44,7 @@ struct ConvK {
   const float* resid;
   float* out_f32;
   __nv_bfloat16* out_bf16;
-  int ob_pad, ob_reflect;
+  int ob_pad, ob_reflect, ob_half;
   int dst_h, dst_w, dst_sy, dst_sx, dst_oy, dst_ox;
   int cout, cout_pad;
   double* stat_sum;
@@ -63,6 +64,10 @@ struct Ring {
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
@@ -367,7 +372,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             if (p.out_bf16) {
               uint32_t w[CW / 2];
 #pragma unroll
-              for (int i = 0; i < CW / 2; i++) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+              for (int i = 0; i < CW / 2; i++) w[i] = p.ob_half ? pack_f16(v[2 * i], v[2 * i + 1]) : pack_bf16(v[2 * i], v[2 * i + 1]);
               for (int a = 0; a < ny; a++)
                 for (int b = 0; b < nx; b++) {
                   __nv_bfloat16* op = p.out_bf16 + (((size_t)n * Hp + ys[a]) * Wp + xs[b]) * p.cout + cb;
@@ -378,7 +383,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   } else {
 #pragma unroll
                     for (int i = 0; i < CW; i++)
-                      if (cb + i < p.cout) op[i] = __float2bfloat16(v[i]);
+                      if (cb + i < p.cout) {
+                        if (p.ob_half) reinterpret_cast<__half*>(op)[i] = __float2half_rn(v[i]);
+                        else op[i] = __float2bfloat16(v[i]);
+                      }
                   }
                 }
             }
@@ -495,6 +503,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   k.out_bf16 = (__nv_bfloat16*)d->out_bf16.ptr;
   k.ob_pad = d->out_bf16.ptr ? d->out_bf16.pad : 0;
   k.ob_reflect = d->out_reflect;
+  k.ob_half = d->out16_is_half;
   k.dst_h = d->dst_h;
   k.dst_w = d->dst_w;
   k.dst_sy = d->dst_sy ? d->dst_sy : 1;

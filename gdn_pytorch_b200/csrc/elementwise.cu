@@ -4,6 +4,7 @@
 //   upsampling / dilation / channel slicing), weight pack / gradient unpack.
 // All tensors are NHWC; 8 bf16 (16 B) or 4 fp32 (16 B) per thread access, grid-stride loops.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace gdn {
@@ -33,6 +34,15 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack8h(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 t = __half22float2(h[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -118,12 +128,13 @@ struct ActFwd {
   float* out_f32;                 // [N][H][W][C] or NULL
   __nv_bfloat16* out_bf16;        // [N][OH+2P][OW+2P][C] or NULL, OH = H*up (or 2H when dilate)
   int P, reflect, up, dilate;     // up: 0 none, 1 bilinear x2 align_corners=False, 2 align_corners=True
+  int src_half;
 };
 
 __device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c8, float* v) {
   if (a.src_bf16) {
     const uint4 u = *reinterpret_cast<const uint4*>(a.src_bf16 + pix * a.C + c8);
-    unpack8(u, v);
+    if (a.src_half) unpack8h(u, v); else unpack8(u, v);
   } else {
     const float4 p0 = *reinterpret_cast<const float4*>(a.src_f32 + pix * a.C + c8);
     const float4 p1 = *reinterpret_cast<const float4*>(a.src_f32 + pix * a.C + c8 + 4);
@@ -240,6 +251,7 @@ struct BnBwd {
   int H, W, dilate;
   float* dgamma;                  // += sum_gx   (may be NULL)
   float* dbeta;                   // += sum_g
+  int raw_half;
 };
 
 
@@ -268,7 +280,8 @@ __global__ void bn_bwd_reduce_kernel(const BnBwd b) {
     }
     for (long long pix = (long long)blockIdx.x * lanes + pl; pix < b.npix; pix += (long long)gridDim.x * lanes) {
       float x[8];
-      unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
+      if (b.raw_half) unpack8h(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
+      else unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
       const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
       const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
       const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -320,7 +333,8 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
       const int y = b.dilate ? (Y >> 1) : Y, x = b.dilate ? (X >> 1) : X;
       const long long pix = (n * b.H + y) * b.W + x;
       float xr[8];
-      unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
+      if (b.raw_half) unpack8h(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
+      else unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
       const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
       const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
       const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -545,6 +559,7 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
   a.out_f32 = d->out_f32;
   a.out_bf16 = (__nv_bfloat16*)d->out_bf16;
   a.P = d->pad; a.reflect = d->reflect; a.up = d->up; a.dilate = d->dilate;
+  a.src_half = d->src16_is_half;
   const long long w1 = a.out_f32 ? (long long)a.N * a.H * a.W * (a.C / 8) : 0;
   const long long w2 = a.out_bf16 ? (long long)a.N * (OH + 2 * a.P) * (OW + 2 * a.P) * (a.C / 8) : 0;
   const long long work = w1 > w2 ? w1 : w2;
@@ -568,6 +583,7 @@ static int fill_bnbwd(const gdn_bn_bwd_desc* d, BnBwd& b) {
   b.dy = (__nv_bfloat16*)d->dy;
   b.H = d->h; b.W = d->w; b.dilate = d->dilate;
   b.dgamma = d->dgamma; b.dbeta = d->dbeta;
+  b.raw_half = d->raw_is_half;
   return GDN_OK;
 }
 

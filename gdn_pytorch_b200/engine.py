@@ -30,14 +30,14 @@ class ActFwdDesc(C.Structure):
     _fields_ = [("src_bf16", C.c_void_p), ("src_f32", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("resid", C.c_void_p), ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c", C.c_int32), ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p), ("pad", C.c_int32),
-                ("reflect", C.c_int32), ("up", C.c_int32), ("dilate", C.c_int32)]
+                ("reflect", C.c_int32), ("up", C.c_int32), ("dilate", C.c_int32), ("src16_is_half", C.c_int32)]
 
 
 class BnBwdDesc(C.Structure):
     _fields_ = [("dact", C.c_void_p), ("raw", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("c", C.c_int32), ("sum_g", C.c_void_p), ("sum_gx", C.c_void_p), ("dy", C.c_void_p),
-                ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+                ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("raw_is_half", C.c_int32)]
 
 
 class FoldDesc(C.Structure):
@@ -307,13 +307,14 @@ class Engine:
             out_vs = self.variants[u.out]
             if self.train and u.bn is not None:
                 # raw conv output + statistics, then BatchNorm apply into every variant the consumers need
-                cu.raw = torch.empty((N, ho, wo, u.cout), dtype=torch.bfloat16, device=dev)
+                cu.raw = torch.empty((N, ho, wo, u.cout), dtype=torch.float16, device=dev)
                 cu.stat = torch.zeros((2, u.cout), dtype=torch.float64, device=dev)
                 cu.scale = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.shift = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.mean = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.rstd = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 d.out_bf16 = Act(cu.raw.data_ptr(), N, ho, wo, u.cout, 0)
+                d.out16_is_half = 1
                 d.stat_sum = cu.stat[0].data_ptr()
                 d.stat_sqsum = cu.stat[1].data_ptr()
                 self.fwd.append(lambda s, cu=cu: cu.stat.zero_())
@@ -338,6 +339,7 @@ class Engine:
                 for v in todo:
                     a = ActFwdDesc()
                     a.src_bf16 = cu.raw.data_ptr()
+                    a.src16_is_half = 1
                     a.scale, a.shift = cu.scale.data_ptr(), cu.shift.data_ptr()
                     a.resid = _ptr(self.f32.get(u.resid)) if u.resid else None
                     a.relu = int(u.relu)
@@ -433,6 +435,7 @@ class Engine:
         assert self.train
         self.bwd = []
         self.pack_ops_bwd = []
+        self.grad_ready_op = {}   # parameter name -> index of the backward op after which its gradient is final
         self.launches_bwd = 0
         # parameter gradients: one flat fp32 buffer, views per parameter in state_dict order
         names = [k for k, t in P.items() if t.dtype == torch.float32 and getattr(t, "requires_grad", False)]
@@ -499,6 +502,7 @@ class Engine:
             b.scale, b.shift, b.mean, b.rstd = (cu.scale.data_ptr(), cu.shift.data_ptr(), cu.mean.data_ptr(),
                                                 cu.rstd.data_ptr())
             b.relu = int(u.relu)
+            b.raw_is_half = 1
             b.n, b.h, b.w, b.c = N, ho, wo, u.cout
             b.sum_g, b.sum_gx = self.bn_sums[0].data_ptr(), self.bn_sums[1].data_ptr()
             b.dy = cu.dy.data_ptr()
@@ -508,6 +512,7 @@ class Engine:
             self.bwd.append(lambda s: self.bn_sums.zero_())
             self.bwd.append(self._call(L.gdn_bn_bwd_reduce, b, "bn_bwd_reduce " + u.conv))
             self.bwd.append(self._call(L.gdn_act_backward, b, "act_backward " + u.conv))
+            self.grad_ready_op[u.bn + ".weight"] = self.grad_ready_op[u.bn + ".bias"] = len(self.bwd) - 1
             self.launches_bwd += 2
             need_dgrad = [s for s in u.srcs if not (s == "in" and self.thin_in)]
             fwd_stride2 = (not u.transposed) and u.stride == 2
@@ -550,6 +555,7 @@ class Engine:
                 if rc:
                     _lib.check(rc, "unpack " + name)
             self.bwd.append(unpack)
+            self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
             self.launches_bwd += 2
             # ---- input gradient(s)
             c_off = 0
@@ -689,6 +695,7 @@ class Engine:
             if rc:
                 _lib.check(rc, "unpack head")
         self.bwd.append(unpack)
+        self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
         self.launches_bwd += 5
         cu.keep = [wdg]
 

@@ -1,0 +1,263 @@
+"""Fused training steps: the per-iteration bodies of the reference's train loops on B200 kernels.
+
+  RtoDTrainStep  = /root/reference/src/trainer.py:696-768  (train_AE_RtoD: model fwd, two frozen no-grad DtoD passes,
+                   masked BerHu + latent MSE + edge-aware smoothness, zero_grad / backward / Adam.step)
+  DtoDTrainStep  = /root/reference/src/trainer.py:427-468  (train_AE_DtoD: model fwd, BerHu + 3*Sobel loss, Adam)
+  Optimizer      = optim.Adam(params, lr, [0.9, 0.999], eps=1e-8, weight_decay=5e-4), GDN_main.py:157,173
+  Data parallel  = replaces nn.DataParallel (GDN_main.py:153-198): one process per GPU, parameters replicated,
+                   per-shard BatchNorm statistics (what DataParallel replicas do), gradient all-reduce (AVG) over
+                   NCCL in ~25 MB buckets launched while the rest of backward is still running, plus one 4-byte
+                   all-reduce(MAX) so the BerHu threshold c = 0.2*max|diff| stays a GLOBAL-batch quantity as in the
+                   reference (loss computed on the gathered batch, trainer.py:711-720).
+
+Nothing here synchronises with the host; losses are returned as 0-dim device tensors.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .module_runtime import get_engine, _engines, _after_train_forward
+from .ops import LossKernels, FusedAdam
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def flatten_parameters(module):
+    """Re-home every parameter of ``module`` into ONE flat fp32 buffer (4-element aligned slots, named_parameters
+    order) so that Adam and the gradient all-reduce are single contiguous operations.  Values are preserved;
+    state_dict()/load_state_dict() keep working (they copy in place).  Returns the flat buffer."""
+    named = list(module.named_parameters())
+    total = sum(_round_up(p.numel(), 4) for _, p in named)
+    dev = named[0][1].device
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)
+    o = 0
+    with torch.no_grad():
+        for _, p in named:
+            n = p.numel()
+            view = flat[o:o + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            o += _round_up(n, 4)
+    module.__dict__.pop("_gdn_engines", None)   # engines hold raw pointers to the old storage
+    return flat
+
+
+class GradBuckets:
+    """Contiguous ~bucket_bytes slices of the flat gradient buffer, ordered by when they become final during
+    backward.  ``ready_after[i]`` is the index of the backward op after which bucket i may be all-reduced."""
+
+    def __init__(self, slots, ready_op, bucket_bytes=25 << 20):
+        """slots: [(name, offset, numel_padded)] in buffer order; ready_op: {name: op index after which final}"""
+        self.buckets = []  # (start, end, ready_after)
+        cur_s, cur_e, cur_r = None, None, -1
+        for name, off, n in slots:
+            if cur_s is None:
+                cur_s, cur_e, cur_r = off, off + n, ready_op.get(name, -1)
+            else:
+                cur_e = off + n
+                cur_r = max(cur_r, ready_op.get(name, -1))
+            if (cur_e - cur_s) * 4 >= bucket_bytes:
+                self.buckets.append((cur_s, cur_e, cur_r))
+                cur_s = None
+        if cur_s is not None:
+            self.buckets.append((cur_s, cur_e, cur_r))
+        self.buckets.sort(key=lambda b: b[2])
+
+
+def allreduce_avg_(flat, buckets, group=None, async_streams=None):
+    """in-place average of ``flat`` across the group, bucket by bucket (host logic shared by the NCCL path and the
+    gloo CPU tests)"""
+    world = dist.get_world_size(group)
+    works = []
+    for s, e, _ in buckets:
+        works.append((dist.all_reduce(flat[s:e], op=dist.ReduceOp.SUM, group=group, async_op=True), s, e))
+    for w, s, e in works:
+        w.wait()
+    flat.mul_(1.0 / world)
+    return flat
+
+
+class _StepBase:
+    def __init__(self, model, lr, betas, eps, weight_decay, group, bucket_mb):
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if self.world > 1:
+            # replicate rank 0's parameters and buffers once (DataParallel re-broadcasts them every forward)
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, src=0, group=group)
+        self.flat_params = flatten_parameters(model)
+        self.graph = model.gdn_graph()
+        model.__dict__["_gdn_graph"] = self.graph
+        self.kern = LossKernels(self.dev)
+        self.lr = lr
+        self.hyper = (betas, eps, weight_decay)
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.eng = None
+        self.opt = None
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        self.step_count = 0
+        self.launches_per_step = 0
+
+    def _ensure(self, x):
+        if self.eng is not None and self.eng.N == x.shape[0] and self.eng.H == x.shape[2] and self.eng.W == x.shape[3]:
+            return
+        self.model.train()
+        _engines(self.model)
+        self.eng = get_engine(self.model, self.graph, x, train=True, backward=True, want=())
+        eng = self.eng
+        named = list(self.model.named_parameters())
+        # the engine's flat gradient uses the same slot layout as flatten_parameters()
+        assert eng.flat_grad.numel() == self.flat_params.numel(), (eng.flat_grad.numel(), self.flat_params.numel())
+        if self.opt is None:
+            betas, eps, wd = self.hyper
+            self.opt = FusedAdam([p for _, p in named], lr=self.lr, betas=betas, eps=eps, weight_decay=wd,
+                                 flat=(self.flat_params, eng.flat_grad))
+        else:
+            self.opt.flat = (self.flat_params, eng.flat_grad)
+        # bucket plan: a parameter's gradient is final after the last backward op that mentions it
+        slots, o = [], 0
+        for n, p in named:
+            slots.append((n, o, _round_up(p.numel(), 4)))
+            o += _round_up(p.numel(), 4)
+        ready = getattr(eng, "grad_ready_op", {})
+        self.buckets = GradBuckets(slots, ready, self.bucket_bytes).buckets
+
+    def set_lr(self, lr):
+        """the reference mutates param_groups[...]['lr'] (trainer.py:784-792); same thing here"""
+        self.lr = lr
+        if self.opt is not None:
+            for g in self.opt.param_groups:
+                g["lr"] = lr
+
+    def _backward_and_reduce(self):
+        eng = self.eng
+        s = _lib.stream_ptr()
+        eng.flat_grad.zero_()
+        if self.world == 1:
+            for op in eng.bwd:
+                op(s)
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        bi = 0
+        nb = len(self.buckets)
+        for i, op in enumerate(eng.bwd):
+            op(s)
+            while bi < nb and self.buckets[bi][2] <= i:
+                self._launch_bucket(bi, cur)
+                bi += 1
+        while bi < nb:
+            self._launch_bucket(bi, cur)
+            bi += 1
+        cur.wait_stream(self.comm_stream)
+
+    def _launch_bucket(self, bi, cur):
+        s0, e0, _ = self.buckets[bi]
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            dist.all_reduce(self.eng.flat_grad[s0:e0], op=dist.ReduceOp.SUM, group=self.group)
+
+    def _optim_step(self):
+        self.step_count += 1
+        self.opt.grad_scale = 1.0 / self.world     # SUM all-reduce -> average, folded into the Adam kernel
+        self.opt.step()
+        self.eng._wversion = None                    # parameters changed through raw pointers: re-pack next forward
+        self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1   # ... in every other engine too
+
+
+class DtoDTrainStep(_StepBase):
+    """one iteration of train_AE_DtoD (trainer.py:411-468)"""
+
+    def __init__(self, model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4, group=None, bucket_mb=25):
+        super().__init__(model, lr, betas, eps, weight_decay, group, bucket_mb)
+
+    def step(self, depths, sparse):
+        """depths: (N,1,H,W) dense gt in [-1,1]; sparse: (N,1|3,H,W) sparse gt (invalid = -1) or None."""
+        self._ensure(depths)
+        eng = self.eng
+        eng.forward(depths)
+        _after_train_forward(self.model)
+        out = eng.depth()
+        self.kern.absdiff_max(out, depths)
+        if self.world > 1:
+            dist.all_reduce(self.kern.maxabs, op=dist.ReduceOp.MAX, group=self.group)
+        self.kern.loss(1, out, depths, sparse, None, dpre=eng.dpre)
+        self._backward_and_reduce()
+        self._optim_step()
+        return self.kern.assemble(1, float(out.numel()))
+
+
+class RtoDTrainStep(_StepBase):
+    """one iteration of train_AE_RtoD (trainer.py:670-768) with a frozen, eval-mode DtoD guidance network"""
+
+    def __init__(self, model, dtod_model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4, group=None,
+                 bucket_mb=25, guidance=True):
+        super().__init__(model, lr, betas, eps, weight_decay, group, bucket_mb)
+        self.dtod = dtod_model
+        self.guidance = guidance and dtod_model is not None
+        if self.guidance:
+            self.dtod.eval()
+            self.dgraph = self.dtod.gdn_graph()
+            self.deng = [None, None]
+
+    def _dtod_features(self, slot, x):
+        """encoder + bottleneck of the frozen DtoD net only: (x1, x2, x4, x6) is all the loss reads (trainer.py:700,703);
+        two engine instances so the target features and the prediction features coexist"""
+        e = self.deng[slot]
+        if e is None or e.N != x.shape[0] or e.H != x.shape[2] or e.W != x.shape[3]:
+            from .engine import Engine
+            from .module_runtime import _params
+            names = self.dgraph.encoder_outputs
+            e = Engine(self.dgraph, _params(self.dtod), x.shape[0], x.shape[2], x.shape[3], train=False, backward=False,
+                       want=names, stop_after=names[-1], device=x.device)
+            self.deng[slot] = e
+        e.forward(x)
+        return [e.value(n) for n in self.dgraph.encoder_outputs]
+
+    def step(self, rgb, depths, sparse):
+        """rgb (N,3,H,W), depths (N,1,H,W), sparse (N,1|3,H,W) or None; all fp32 in [-1,1] on the GPU."""
+        self._ensure(rgb)
+        eng = self.eng
+        eng.forward(rgb)
+        _after_train_forward(self.model)
+        out = eng.depth()
+        feat_numels = None
+        self.kern.absdiff_max(out, depths)
+        if self.world > 1:
+            dist.all_reduce(self.kern.maxabs, op=dist.ReduceOp.MAX, group=self.group)
+        self.kern.loss(0, out, depths, sparse, rgb, dpre=eng.dpre)
+        if self.guidance:
+            with torch.no_grad():
+                ft_tar = self._dtod_features(0, depths)
+                ft = self._dtod_features(1, out)
+            self.kern.latent(ft, ft_tar)
+            feat_numels = [float(t.numel()) for t in ft]
+        self._backward_and_reduce()
+        self._optim_step()
+        return self.kern.assemble(0, float(out.numel()), feat_numels)
+
+
+def init_distributed_from_env():
+    """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*); returns (rank, world, device)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+    else:
+        dev = torch.device("cpu")
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    return rank, world, dev

@@ -74,6 +74,8 @@ typedef struct {
   int32_t dst_sy, dst_sx, dst_oy, dst_ox;
   double* stat_sum;          /* [cout] += sum over pixels of acc, or NULL */
   double* stat_sqsum;        /* [cout] += sum of acc^2 */
+  int32_t out16_is_half;     /* store out_bf16 as IEEE fp16 instead (pre-BatchNorm conv outputs: they only feed
+                                elementwise kernels, and fp16's 10-bit mantissa keeps BN's mean subtraction accurate) */
 } gdn_conv_desc;
 
 int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream);
@@ -119,6 +121,7 @@ typedef struct {
   float* out_f32;
   void* out_bf16;
   int32_t pad, reflect, up, dilate;
+  int32_t src16_is_half;    /* src_bf16 holds fp16 (raw conv output written with out16_is_half) */
 } gdn_act_fwd_desc;
 int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream);
 
@@ -140,6 +143,7 @@ typedef struct {
   int32_t dilate;
   float* dgamma;
   float* dbeta;
+  int32_t raw_is_half;
 } gdn_bn_bwd_desc;
 int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream);
 int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream);

@@ -7,7 +7,9 @@ import torch
 import torch.nn.functional as F
 
 
-def run_graph(graph, sd, x, train=False, bf16=False, stop_after=None):
+def run_graph(graph, sd, x, train=False, bf16=False, stop_after=None, relu_masks=None):
+    """relu_masks: optional {tensor name: bool mask}; when given, ReLU of that unit is applied as y*mask so that a
+    backward comparison is not dominated by sign flips of near-zero pre-activations (bf16 forward noise)."""
     def r(t):
         return t.to(torch.bfloat16).to(torch.float32) if bf16 else t
 
@@ -31,13 +33,16 @@ def run_graph(graph, sd, x, train=False, bf16=False, stop_after=None):
             if train:
                 mean = y.mean((0, 2, 3))
                 var = y.var((0, 2, 3), unbiased=False)
-                ys = r(y)
+                ys = y.to(torch.float16).to(torch.float32) if bf16 else y   # device stores the raw conv output as fp16
                 y = (ys - mean[None, :, None, None]) * torch.rsqrt(var + 1e-5)[None, :, None, None]
                 y = y * g[None, :, None, None] + b[None, :, None, None]
             else:
                 y = F.batch_norm(y, sd[u.bn + ".running_mean"], sd[u.bn + ".running_var"], g, b, False, 0.1, 1e-5)
         if u.relu:
-            y = F.relu(y)
+            if relu_masks is not None and u.out in relu_masks:
+                y = y * relu_masks[u.out].to(y.dtype)
+            else:
+                y = F.relu(y)
         if u.resid:
             y = y + T[u.resid]
         if u.tanh:

@@ -50,7 +50,7 @@ class Ctx:
                 # device path: statistics from the fp32 accumulators, normalisation of the bf16-stored value
                 mean = x.mean((0, 2, 3))
                 var = x.var((0, 2, 3), unbiased=False)
-                xs = _r(x, True)
+                xs = x.to(torch.float16).to(torch.float32)   # raw conv outputs are stored as fp16 on the device
                 y = (xs - mean[None, :, None, None]) * torch.rsqrt(var + EPS)[None, :, None, None]
                 y = y * sd[key + ".weight"][None, :, None, None] + sd[key + ".bias"][None, :, None, None]
                 if self.update_running:
