@@ -131,7 +131,7 @@ struct ActFwd {
   int src_half;
 };
 
-__device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c8, float* v) {
+__device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c8, float* v, const float* sc, const float* sh) {
   if (a.src_bf16) {
     const uint4 u = *reinterpret_cast<const uint4*>(a.src_bf16 + pix * a.C + c8);
     if (a.src_half) unpack8h(u, v); else unpack8(u, v);
@@ -142,7 +142,7 @@ __device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c
   }
   if (a.scale) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], __ldg(a.scale + c8 + j), __ldg(a.shift + c8 + j));
+    for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], sc[j], sh[j]);
   }
   if (a.relu) {
 #pragma unroll
@@ -177,12 +177,22 @@ __global__ void act_forward_kernel(const ActFwd a) {
   const int Hp = OH + 2 * a.P, Wp = OW + 2 * a.P;
   const long long n_b16 = a.out_bf16 ? (long long)a.N * Hp * Wp * cg : 0;
   const long long total = n_f32 > n_b16 ? n_f32 : n_b16;
+  // blockDim.x is a multiple of cg (host-checked): a thread keeps its 8 channels over the grid-stride loop
+  float sc[8], sh[8];
+  {
+    const int c8 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % cg) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      sc[j] = a.scale ? a.scale[c8 + j] : 1.f;
+      sh[j] = a.scale ? a.shift[c8 + j] : 0.f;
+    }
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (i < n_f32) {
       const int c8 = (int)(i % cg) * 8;
       const long long pix = i / cg;
       float v[8];
-      act_value8(a, pix, c8, v);
+      act_value8(a, pix, c8, v, sc, sh);
       float* o = a.out_f32 + pix * a.C + c8;
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -205,7 +215,7 @@ __global__ void act_forward_kernel(const ActFwd a) {
 #pragma unroll
           for (int j = 0; j < 8; j++) v[j] = 0.f;
         } else {
-          act_value8(a, ((long long)n * a.H + (Y >> 1)) * a.W + (X >> 1), c8, v);
+          act_value8(a, ((long long)n * a.H + (Y >> 1)) * a.W + (X >> 1), c8, v, sc, sh);
         }
       } else if (a.up) {
         int y0, y1, x0, x1;
@@ -214,10 +224,10 @@ __global__ void act_forward_kernel(const ActFwd a) {
         up_coord(X, a.W, a.up, x0, x1, wx);
         float v00[8], v01[8], v10[8], v11[8];
         const long long base = (long long)n * a.H;
-        act_value8(a, (base + y0) * a.W + x0, c8, v00);
-        act_value8(a, (base + y0) * a.W + x1, c8, v01);
-        act_value8(a, (base + y1) * a.W + x0, c8, v10);
-        act_value8(a, (base + y1) * a.W + x1, c8, v11);
+        act_value8(a, (base + y0) * a.W + x0, c8, v00, sc, sh);
+        act_value8(a, (base + y0) * a.W + x1, c8, v01, sc, sh);
+        act_value8(a, (base + y1) * a.W + x0, c8, v10, sc, sh);
+        act_value8(a, (base + y1) * a.W + x1, c8, v11, sc, sh);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           // same association as ATen's upsample_bilinear2d: w(1-wy)*(row0 blend) + wy*(row1 blend)
@@ -226,7 +236,7 @@ __global__ void act_forward_kernel(const ActFwd a) {
           v[j] = (1.f - wy) * top + wy * bot;
         }
       } else {
-        act_value8(a, ((long long)n * a.H + Y) * a.W + X, c8, v);
+        act_value8(a, ((long long)n * a.H + Y) * a.W + X, c8, v, sc, sh);
       }
       *reinterpret_cast<uint4*>(a.out_bf16 + (((long long)n * Hp + yp) * Wp + xp) * a.C + c8) = pack8(v);
     }
@@ -318,8 +328,19 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
       b.dbeta[c] += (float)(b.sum_g[c]);
     }
   }
+  // blockDim.x (256) is a multiple of cg, so every thread keeps the same 8 channels over the grid-stride loop
+  const int c8 = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % cg) * 8;
+  float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = b.scale[c8 + j];
+    sh[j] = b.shift[c8 + j];
+    mu[j] = b.mean[c8 + j];
+    rs[j] = b.rstd[c8 + j];
+    m1[j] = (float)(b.sum_g[c8 + j] * inv_n);
+    m2[j] = (float)(b.sum_gx[c8 + j] * inv_n);
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg) * 8;
     long long t = i / cg;
     const int X = (int)(t % OW);
     t /= OW;
@@ -340,13 +361,10 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
       const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const int c = c8 + j;
-        const float sc = __ldg(b.scale + c), sh = __ldg(b.shift + c);
         float gq = d[j];
-        if (b.relu && fmaf(xr[j], sc, sh) <= 0.f) gq = 0.f;
-        const float xh = (xr[j] - __ldg(b.mean + c)) * __ldg(b.rstd + c);
-        const float m1 = (float)(b.sum_g[c] * inv_n), m2 = (float)(b.sum_gx[c] * inv_n);
-        o[j] = sc * (gq - m1 - xh * m2);
+        if (b.relu && fmaf(xr[j], sc[j], sh[j]) <= 0.f) gq = 0.f;
+        const float xh = (xr[j] - mu[j]) * rs[j];
+        o[j] = sc[j] * (gq - m1[j] - xh * m2[j]);
       }
     }
     *reinterpret_cast<uint4*>(b.dy + i * 8) = pack8(o);
@@ -544,7 +562,8 @@ GDN_API int gdn_bn_fold(const float* gamma, const float* beta, const float* rmea
 
 GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
   if (!d || (!d->src_bf16 == !d->src_f32)) return fail(GDN_INVALID_DESC, "gdn_act_forward: exactly one source required");
-  if (d->c % 8) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_forward: channels %d not a multiple of 8", d->c);
+  if (d->c % 8 || (kEwThreads % (d->c / 8)))
+    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_forward: channels %d (need a multiple of 8 whose /8 divides %d)", d->c, kEwThreads);
   if (d->up && d->dilate) return fail(GDN_INVALID_DESC, "gdn_act_forward: up and dilate are exclusive");
   const int OH = (d->up || d->dilate) ? 2 * d->h : d->h, OW = (d->up || d->dilate) ? 2 * d->w : d->w;
   if (d->reflect && (d->pad >= OH || d->pad >= OW)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_forward: reflection pad too large");

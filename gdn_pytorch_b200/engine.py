@@ -186,6 +186,7 @@ class Engine:
             rc = fn(C.byref(desc), s)
             if rc:
                 _lib.check(rc, what)
+        run.label = what
         return run
 
     def _pack_call(self, pd, wt, scale, out, what, w_off=0):
@@ -698,6 +699,20 @@ class Engine:
         self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
         self.launches_bwd += 5
         cu.keep = [wdg]
+
+    def profile(self, ops, reps=3):
+        """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid"""
+        s = _lib.stream_ptr()
+        evs = []
+        for op in ops:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                op(s)
+            e1.record()
+            evs.append((getattr(op, "label", "misc"), e0, e1))
+        torch.cuda.synchronize()
+        return [(n, a.elapsed_time(b) / reps) for n, a, b in evs]
 
     def backward(self, dpre=None, dout_nhwc=None):
         """dpre: dL/d(pre-tanh output), fp32 (N, H, W) -- or None if the loss kernel already wrote self.dpre.
