@@ -214,50 +214,58 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == kWarpMMA) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      Ring ra, rb, rc;
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
-      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
-        tc_fence_after();
-        const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride);
-        for (int c = 0; c < chunks; c++) {
-          if (halo) {
-            mbar_wait(&a_full[ra.i], ra.ph);
-          }
-          for (int r = 0; r < p.kh; r++)
-            for (int s = 0; s < p.kw; s++) {
-              if (!halo) mbar_wait(&a_full[ra.i], ra.ph);
-              mbar_wait(&b_full[rb.i], rb.ph);
-              tc_fence_after();
-              const uint32_t a0 = sA_u + (uint32_t)ra.i * p.a_bytes + (halo ? (uint32_t)(r * p.halo_w + s) * 128u : 0u);
-              const uint32_t b0 = sB_u + (uint32_t)rb.i * B_BYTES;
-              const uint32_t first = (c == 0 && r == 0 && s == 0) ? 0u : 1u;
-              for (int j = 0; j < p.J; j++) {
+    // The WHOLE warp runs this (warp-uniform) loop so that descriptors live in uniform registers; one elected
+    // lane issues all MMAs of a (tap, chunk) step back to back as "64-bit descriptor base + immediate"
+    // (one UIADD3.64 + one UTCHMMA per MMA -- see tools/probe_mma_rate.cu for the issue-rate measurements).
+    Ring ra, rb, rc;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
+    const uint64_t a_hi = make_smem_desc_sw128(0, 0, a_sbo);
+    const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    const int J = p.J;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride);
+      for (int c = 0; c < chunks; c++) {
+        if (halo) mbar_wait(&a_full[ra.i], ra.ph);
+        for (int r = 0; r < p.kh; r++)
+          for (int s = 0; s < p.kw; s++) {
+            if (!halo) mbar_wait(&a_full[ra.i], ra.ph);
+            mbar_wait(&b_full[rb.i], rb.ph);
+            tc_fence_after();
+            const uint32_t a0 = sA_u + (uint32_t)ra.i * p.a_bytes + (halo ? (uint32_t)(r * p.halo_w + s) * 128u : 0u);
+            const uint64_t ad0 = a_hi + (uint64_t)((a0 & 0x3FFFFu) >> 4);
+            const uint64_t bd0 = b_hi + (uint64_t)(((sB_u + (uint32_t)rb.i * B_BYTES) & 0x3FFFFu) >> 4);
+            const uint32_t first = (c == 0 && r == 0 && s == 0) ? 0u : 1u;
+            if (elect_one()) {
+              // sub-tile j is 8 pixels (1024 B) further along the halo row; K advances 32 B per 16-channel step
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                  const uint64_t ad = make_smem_desc_sw128(a0 + (uint32_t)j * 1024u + k4 * 32u, 0, a_sbo);
-                  const uint64_t bd = make_smem_desc_sw128(b0 + k4 * 32u, 0, 1024u);
-                  umma_bf16(acc_addr + (uint32_t)(j * BN), ad, bd, idesc, first | (uint32_t)k4);
+              for (int j = 0; j < 4; j++) {
+                if (j < J) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; k4++)
+                    umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
+                              idesc, first | (uint32_t)k4);
                 }
               }
               umma_commit(&b_empty[rb.i]);
-              rb.next(p.nbst);
-              if (!halo) {
-                umma_commit(&a_empty[ra.i]);
-                ra.next(p.na);
-              }
+              if (!halo) umma_commit(&a_empty[ra.i]);
             }
-          if (halo) {
-            umma_commit(&a_empty[ra.i]);
-            ra.next(p.na);
+            __syncwarp();
+            rb.next(p.nbst);
+            if (!halo) ra.next(p.na);
           }
+        if (halo) {
+          if (elect_one()) umma_commit(&a_empty[ra.i]);
+          __syncwarp();
+          ra.next(p.na);
         }
-        umma_commit(&acc_full[rc.i]);
-        rc.next(p.acc_bufs);
       }
+      if (elect_one()) umma_commit(&acc_full[rc.i]);
+      __syncwarp();
+      rc.next(p.acc_bufs);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0..3

@@ -194,66 +194,78 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
       }
     }
   } else if (warp == kWgWarpMMA) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      WRing rx, ry;
-      uint32_t accph = 0;
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
-      const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
-      const uint32_t x_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        int g, cic, cob, pt0, pt1;
-        decode_work(w, g, cic, cob, pt0, pt1);
-        const int u0 = g * p.units_per_cta;
-        const int u1 = min(u0 + p.units_per_cta, p.n_units);
-        mbar_wait(&acc_empty, accph ^ 1);
-        tc_fence_after();
-        for (int t = pt0; t < pt1; t++) {
-          mbar_wait(&y_full[ry.i], ry.ph);
-          const uint32_t yb = sY_u + (uint32_t)ry.i * p.y_bytes;
-          if (halo) {
-            mbar_wait(&x_full[rx.i], rx.ph);
-            tc_fence_after();
-            const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
-            for (int u = u0; u < u1; u++) {
-              const WgUnit un = p.units[u];
-              const uint32_t a0 = xb + (uint32_t)(un.rA * p.halo_w + un.sA) * 128u;
-              const uint32_t lbo = un.sB < 0 ? 128u : (uint32_t)((un.rB - un.rA) * p.halo_w + (un.sB - un.sA)) * 128u;
-              const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
-              for (int j = 0; j < p.J; j++) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    WRing rx, ry;
+    uint32_t accph = 0;
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
+    const uint32_t x_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
+    const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
+    const uint64_t a_hi_tap = make_smem_desc_sw128(0, 16384u, 1024u);
+    const int J = p.J;
+    const uint32_t kstep = halo ? (uint32_t)(2 * p.halo_w * 128) >> 4 : (2048u >> 4);  // 16 pixels of K per MMA
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      int g, cic, cob, pt0, pt1;
+      decode_work(w, g, cic, cob, pt0, pt1);
+      const int u0 = g * p.units_per_cta;
+      const int u1 = min(u0 + p.units_per_cta, p.n_units);
+      mbar_wait(&acc_empty, accph ^ 1);
+      tc_fence_after();
+      for (int t = pt0; t < pt1; t++) {
+        mbar_wait(&y_full[ry.i], ry.ph);
+        const uint32_t yb = sY_u + (uint32_t)ry.i * p.y_bytes;
+        const uint64_t bd0 = b_hi + (uint64_t)((yb & 0x3FFFFu) >> 4);
+        const uint32_t first_t = (t > pt0) ? 1u : 0u;
+        if (halo) {
+          mbar_wait(&x_full[rx.i], rx.ph);
+          tc_fence_after();
+          const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
+          for (int u = u0; u < u1; u++) {
+            const WgUnit un = p.units[u];
+            const uint32_t a0 = xb + (uint32_t)(un.rA * p.halo_w + un.sA) * 128u;
+            const uint32_t lbo = un.sB < 0 ? 128u : (uint32_t)((un.rB - un.rA) * p.halo_w + (un.sB - un.sA)) * 128u;
+            const uint64_t ad0 = make_smem_desc_sw128(a0, lbo, x_sbo);
+            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++) {
-                  // K step = 16 pixels = two 8-pixel rows of the tile
-                  const uint64_t ad = make_smem_desc_sw128(a0 + (uint32_t)(2 * ks * p.halo_w + 8 * j) * 128u, lbo, x_sbo);
-                  const uint64_t bd = make_smem_desc_sw128(yb + (uint32_t)j * 16384u + ks * 2048u, 0, 1024u);
-                  umma_bf16(acc, ad, bd, idesc, (t > pt0 || j > 0 || ks > 0) ? 1u : 0u);
+              for (int j = 0; j < 2; j++) {
+                if (j < J) {
+#pragma unroll
+                  for (int ks = 0; ks < 8; ks++)
+                    umma_bf16(acc, ad0 + (uint64_t)(ks * kstep + j * 64), bd0 + (uint64_t)(j * 1024 + ks * 128), idesc,
+                              first_t | (uint32_t)(j | ks));
                 }
               }
             }
-            umma_commit(&x_empty[rx.i]);
-            rx.next(p.nstage);
-          } else {
-            for (int u = u0; u < u1; u++) {
-              mbar_wait(&x_full[rx.i], rx.ph);
-              tc_fence_after();
-              const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
-              const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
-#pragma unroll
-              for (int ks = 0; ks < 8; ks++) {
-                const uint64_t ad = make_smem_desc_sw128(xb + ks * 2048u, 16384u, 1024u);
-                const uint64_t bd = make_smem_desc_sw128(yb + ks * 2048u, 0, 1024u);
-                umma_bf16(acc, ad, bd, idesc, (t > pt0 || ks > 0) ? 1u : 0u);
-              }
-              umma_commit(&x_empty[rx.i]);
-              rx.next(p.nstage);
-            }
+            __syncwarp();
           }
-          umma_commit(&y_empty[ry.i]);
-          ry.next(p.nstage);
+          if (elect_one()) umma_commit(&x_empty[rx.i]);
+          __syncwarp();
+          rx.next(p.nstage);
+        } else {
+          for (int u = u0; u < u1; u++) {
+            mbar_wait(&x_full[rx.i], rx.ph);
+            tc_fence_after();
+            const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
+            const uint64_t ad0 = a_hi_tap + (uint64_t)((xb & 0x3FFFFu) >> 4);
+            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ks++)
+                umma_bf16(acc, ad0 + (uint64_t)(ks * 128), bd0 + (uint64_t)(ks * 128), idesc, first_t | (uint32_t)ks);
+              umma_commit(&x_empty[rx.i]);
+            }
+            __syncwarp();
+            rx.next(p.nstage);
+          }
         }
-        umma_commit(&acc_full);
-        accph ^= 1;
+        if (elect_one()) umma_commit(&y_empty[ry.i]);
+        __syncwarp();
+        ry.next(p.nstage);
       }
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
+      accph ^= 1;
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> fp32 atomics

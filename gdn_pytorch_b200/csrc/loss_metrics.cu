@@ -392,7 +392,11 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
 //   g += wd*p ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
-                            float eps, float wd, float grad_scale) {
+                            float eps, float wd, float grad_scale, const float* __restrict__ dyn) {
+  if (dyn) {  // step-dependent scalars kept in device memory so that a captured CUDA graph stays valid
+    step_size = dyn[0];
+    inv_sqrt_bc2 = dyn[1];
+  }
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -499,7 +503,17 @@ GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t 
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_size, inv_sqrt_bc2, beta1,
-                                                                       beta2, eps, weight_decay, grad_scale);
+                                                                       beta2, eps, weight_decay, grad_scale, nullptr);
+  GDN_LAUNCH_CHECK("adam_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, const float* dyn, float beta1,
+                              float beta2, float eps, float weight_decay, float grad_scale, gdn_stream stream) {
+  if (!p || !g || !m || !v || !dyn || n < 0) return fail(GDN_INVALID_DESC, "gdn_adam_step_dyn: bad arguments");
+  if (n == 0) return GDN_OK;
+  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, 0.f, beta1, beta2, eps,
+                                                                       weight_decay, grad_scale, dyn);
   GDN_LAUNCH_CHECK("adam_kernel");
   return GDN_OK;
 }

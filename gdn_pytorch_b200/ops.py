@@ -131,10 +131,26 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.flat = flat
+        self.dyn = None            # optional device float[2] (step size, 1/sqrt(bias correction 2)), see set_dyn()
+        self._dyn_host = None
         self._flat_state = None
         self._step = 0
         self.grad_scale = 1.0
         self.L = _lib.lib()
+
+    def set_dyn(self, step):
+        """write the scalars of Adam step number ``step`` (1-based) into device memory (async H2D from pinned)"""
+        import math
+        g = self.param_groups[0]
+        if self.dyn is None:
+            dev = self.flat[0].device
+            self.dyn = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        bc1 = 1.0 - g["betas"][0] ** step
+        bc2 = 1.0 - g["betas"][1] ** step
+        self._dyn_host[0] = g["lr"] / bc1
+        self._dyn_host[1] = 1.0 / math.sqrt(bc2)
+        self.dyn.copy_(self._dyn_host, non_blocking=True)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -147,6 +163,14 @@ class FusedAdam(torch.optim.Optimizer):
                 self._flat_state = (torch.zeros_like(fp), torch.zeros_like(fp))
             m, v = self._flat_state
             g = self.param_groups[0]
+            if self.dyn is not None:
+                # step-dependent scalars live in device memory (written by set_dyn() outside a captured graph)
+                rc = L.gdn_adam_step_dyn(C.c_void_p(fp.data_ptr()), C.c_void_p(fg.data_ptr()), C.c_void_p(m.data_ptr()),
+                                         C.c_void_p(v.data_ptr()), C.c_int64(fp.numel()), C.c_void_p(self.dyn.data_ptr()),
+                                         C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),
+                                         C.c_float(g["weight_decay"]), C.c_float(self.grad_scale), _lib.stream_ptr())
+                _lib.check(rc, "adam_step_dyn(flat)")
+                return loss
             rc = L.gdn_adam_step(C.c_void_p(fp.data_ptr()), C.c_void_p(fg.data_ptr()), C.c_void_p(m.data_ptr()),
                                  C.c_void_p(v.data_ptr()), C.c_int64(fp.numel()), C.c_float(g["lr"]),
                                  C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),

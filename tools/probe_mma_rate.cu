@@ -8,7 +8,7 @@
 using namespace gdn;
 
 __global__ void __launch_bounds__(128, 1)
-rate_kernel(int N, int iters, uint32_t a_sbo, uint32_t a_shift, int nacc, int mn_major, long long* out) {
+rate_kernel(int N, int iters, uint32_t a_sbo, uint32_t a_shift, int nacc, int mn_major, long long* out, int whole_warp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -20,7 +20,35 @@ rate_kernel(int N, int iters, uint32_t a_sbo, uint32_t a_shift, int nacc, int mn
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (threadIdx.x == 0) {
+  if (whole_warp && threadIdx.x < 32) {
+    // the WHOLE warp runs the (warp-uniform) loop; one elected lane issues a whole tap's MMAs at once, with
+    // descriptors formed as 64-bit base + immediate so that everything stays in uniform registers
+    const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
+    const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 128 * 1024;
+    const uint64_t a_hi = make_smem_desc_sw128(0, mn_major ? 128 : 0, a_sbo);
+    const uint64_t b_hi = make_smem_desc_sw128(0, 8192, 1024);
+    const uint32_t tb = tmem_base;
+    const uint32_t accstep = (nacc > 1) ? (uint32_t)N : 0u;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+      const uint32_t tap = (it % 9) * 128u * a_shift;
+      const uint64_t a0 = a_hi + ((sA + tap) >> 4);
+      const uint64_t b0 = b_hi + (sB >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; k4++) umma_bf16(tb + j * accstep, a0 + (j * 64 + k4 * 2), b0 + k4 * 2, idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  } else if (!whole_warp && threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N, mn_major, mn_major);
     const uint32_t sA = smem_u32(smem), sB = smem_u32(smem) + 128 * 1024;
     long long t0 = clock64();
@@ -64,8 +92,9 @@ int main() {
       {16, 5120, 1, 4, 0, "N=16  halo window (head)"},
   };
   for (auto& c : cfgs) {
-    for (int grid : {1, 148}) {
-      rate_kernel<<<grid, 128, 201 * 1024 + 1024>>>(c.N, iters, c.sbo, c.shift, c.nacc, c.mn, d);
+    for (int ww = 0; ww < 2; ww++) {
+      const int grid = 148;
+      rate_kernel<<<grid, 128, 201 * 1024 + 1024>>>(c.N, iters, c.sbo, c.shift, c.nacc, c.mn, d, ww);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("%s: %s\n", c.name, cudaGetErrorString(e)); return 1; }
       long long h[148];
@@ -74,7 +103,7 @@ int main() {
       for (int i = 0; i < grid; i++) avg += (double)h[i];
       avg /= grid;
       const double per = avg / (iters * 16.0);
-      printf("%-48s grid %3d: %7.1f cycles / MMA  (ideal %5.1f) -> %.0f%% of the tensor pipe\n", c.name, grid, per,
+      printf("%-48s %s: %7.1f cycles / MMA  (ideal %5.1f) -> %.0f%% of the tensor pipe\n", c.name, ww ? "warp+elect" : "lane0     ", per,
              128.0 * c.N / 256.0, 100.0 * (128.0 * c.N / 256.0) / per);
     }
   }
