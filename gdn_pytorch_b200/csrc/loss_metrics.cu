@@ -392,10 +392,12 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
 //   g += wd*p ; m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
-                            float eps, float wd, float grad_scale, const float* __restrict__ dyn) {
-  if (dyn) {  // step-dependent scalars kept in device memory so that a captured CUDA graph stays valid
-    step_size = dyn[0];
-    inv_sqrt_bc2 = dyn[1];
+                            float eps, float wd, float grad_scale, const float* __restrict__ dyn, double b1d,
+                            double b2d) {
+  if (dyn) {  // learning rate and step count live in device memory so that a captured CUDA graph stays valid
+    const double t = (double)dyn[1];
+    step_size = (float)((double)dyn[0] / (1.0 - pow(b1d, t)));
+    inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(b2d, t)));
   }
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -503,17 +505,20 @@ GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t 
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_size, inv_sqrt_bc2, beta1,
-                                                                       beta2, eps, weight_decay, grad_scale, nullptr);
+                                                                       beta2, eps, weight_decay, grad_scale, nullptr, 0.0, 0.0);
   GDN_LAUNCH_CHECK("adam_kernel");
   return GDN_OK;
 }
 
-GDN_API int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, const float* dyn, float beta1,
-                              float beta2, float eps, float weight_decay, float grad_scale, gdn_stream stream) {
+__global__ void adam_tick_kernel(float* dyn) { dyn[1] += 1.0f; }
+
+GDN_API int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, float* dyn, double beta1,
+                              double beta2, float eps, float weight_decay, float grad_scale, gdn_stream stream) {
   if (!p || !g || !m || !v || !dyn || n < 0) return fail(GDN_INVALID_DESC, "gdn_adam_step_dyn: bad arguments");
   if (n == 0) return GDN_OK;
-  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, 0.f, beta1, beta2, eps,
-                                                                       weight_decay, grad_scale, dyn);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dyn);
+  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, 0.f, (float)beta1, (float)beta2,
+                                                                       eps, weight_decay, grad_scale, dyn, beta1, beta2);
   GDN_LAUNCH_CHECK("adam_kernel");
   return GDN_OK;
 }

@@ -131,26 +131,25 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.flat = flat
-        self.dyn = None            # optional device float[2] (step size, 1/sqrt(bias correction 2)), see set_dyn()
-        self._dyn_host = None
+        self.dyn = None            # optional device float[2] = (lr, steps taken), see enable_device_step()
         self._flat_state = None
         self._step = 0
         self.grad_scale = 1.0
         self.L = _lib.lib()
 
-    def set_dyn(self, step):
-        """write the scalars of Adam step number ``step`` (1-based) into device memory (async H2D from pinned)"""
-        import math
-        g = self.param_groups[0]
+    def enable_device_step(self):
+        """keep (lr, step count) in a 2-float device buffer: nothing step-dependent is passed by value any more,
+        so the optimizer launch can be captured in a CUDA graph"""
         if self.dyn is None:
-            dev = self.flat[0].device
-            self.dyn = torch.zeros(2, dtype=torch.float32, device=dev)
-            self._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        bc1 = 1.0 - g["betas"][0] ** step
-        bc2 = 1.0 - g["betas"][1] ** step
-        self._dyn_host[0] = g["lr"] / bc1
-        self._dyn_host[1] = 1.0 / math.sqrt(bc2)
-        self.dyn.copy_(self._dyn_host, non_blocking=True)
+            self.dyn = torch.tensor([self.param_groups[0]["lr"], float(self._step)], dtype=torch.float32,
+                                    device=self.flat[0].device)
+        return self.dyn
+
+    def set_lr(self, lr):
+        for g in self.param_groups:
+            g["lr"] = lr
+        if self.dyn is not None:
+            self.dyn[0:1].fill_(lr)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -167,7 +166,7 @@ class FusedAdam(torch.optim.Optimizer):
                 # step-dependent scalars live in device memory (written by set_dyn() outside a captured graph)
                 rc = L.gdn_adam_step_dyn(C.c_void_p(fp.data_ptr()), C.c_void_p(fg.data_ptr()), C.c_void_p(m.data_ptr()),
                                          C.c_void_p(v.data_ptr()), C.c_int64(fp.numel()), C.c_void_p(self.dyn.data_ptr()),
-                                         C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),
+                                         C.c_double(g["betas"][0]), C.c_double(g["betas"][1]), C.c_float(g["eps"]),
                                          C.c_float(g["weight_decay"]), C.c_float(self.grad_scale), _lib.stream_ptr())
                 _lib.check(rc, "adam_step_dyn(flat)")
                 return loss

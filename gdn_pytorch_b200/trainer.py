@@ -82,6 +82,14 @@ def allreduce_avg_(flat, buckets, group=None, async_streams=None):
 
 
 class _StepBase:
+    """shared machinery of the fused steps: flat parameters, bucketed all-reduce, fused Adam, CUDA-graph replay.
+
+    CUDA graph: after ``graph_warmup`` eager steps the whole step (weight re-pack, forward, guidance passes, loss,
+    backward, Adam) is captured ONCE and then replayed -- ~600 kernel launches become one cudaGraphLaunch, which
+    removes the host from the critical path.  Step-dependent Adam scalars and the learning rate live in a 2-float
+    device buffer refreshed before each replay.  Set GDN_GRAPH=0 to run eagerly."""
+    graph_warmup = 2
+
     def __init__(self, model, lr, betas, eps, weight_decay, group, bucket_mb):
         self.model = model
         self.dev = next(model.parameters()).device
@@ -105,6 +113,11 @@ class _StepBase:
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
         self.step_count = 0
         self.launches_per_step = 0
+        env = os.environ.get("GDN_GRAPH")
+        self.use_graph = (env != "0") if env is not None else (self.world == 1)
+        self._graph = None
+        self._static_in = None
+        self._static_out = None
 
     def _ensure(self, x):
         if self.eng is not None and self.eng.N == x.shape[0] and self.eng.H == x.shape[2] and self.eng.W == x.shape[3]:
@@ -134,8 +147,7 @@ class _StepBase:
         """the reference mutates param_groups[...]['lr'] (trainer.py:784-792); same thing here"""
         self.lr = lr
         if self.opt is not None:
-            for g in self.opt.param_groups:
-                g["lr"] = lr
+            self.opt.set_lr(lr)
 
     def _backward_and_reduce(self):
         eng = self.eng
@@ -166,9 +178,38 @@ class _StepBase:
             self.comm_stream.wait_event(ev)
             dist.all_reduce(self.eng.flat_grad[s0:e0], op=dist.ReduceOp.SUM, group=self.group)
 
-    def _optim_step(self):
+    def _run(self, inputs):
+        """eager for the first steps, then capture-and-replay"""
+        shapes = tuple(None if t is None else tuple(t.shape) for t in inputs)
+        if not self.use_graph:
+            self.step_count += 1
+            return self._eager(*inputs)
+        if self._graph is not None and shapes != self._graph_shapes:
+            self._graph = None          # new batch shape: fall back to eager warm-up and re-capture
+            self._eager_done = 0
+        if self._graph is None and getattr(self, "_eager_done", 0) < self.graph_warmup:
+            self._eager_done = getattr(self, "_eager_done", 0) + 1
+            self.step_count += 1
+            return self._eager(*inputs)
         self.step_count += 1
+        if self._graph is None:
+            self._static_in = [None if t is None else t.clone() for t in inputs]
+            self._graph_shapes = shapes
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._static_out = self._eager(*self._static_in)
+            self._graph = g
+        for st, t in zip(self._static_in, inputs):
+            if st is not None and st.data_ptr() != t.data_ptr():
+                st.copy_(t, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def _optim_step(self):
         self.opt.grad_scale = 1.0 / self.world     # SUM all-reduce -> average, folded into the Adam kernel
+        if self.use_graph:
+            self.opt.enable_device_step()
         self.opt.step()
         self.eng._wversion = None                    # parameters changed through raw pointers: re-pack next forward
         self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1   # ... in every other engine too
@@ -182,6 +223,9 @@ class DtoDTrainStep(_StepBase):
 
     def step(self, depths, sparse):
         """depths: (N,1,H,W) dense gt in [-1,1]; sparse: (N,1|3,H,W) sparse gt (invalid = -1) or None."""
+        return self._run((depths, sparse))
+
+    def _eager(self, depths, sparse):
         self._ensure(depths)
         eng = self.eng
         eng.forward(depths)
@@ -225,6 +269,9 @@ class RtoDTrainStep(_StepBase):
 
     def step(self, rgb, depths, sparse):
         """rgb (N,3,H,W), depths (N,1,H,W), sparse (N,1|3,H,W) or None; all fp32 in [-1,1] on the GPU."""
+        return self._run((rgb, depths, sparse))
+
+    def _eager(self, rgb, depths, sparse):
         self._ensure(rgb)
         eng = self.eng
         eng.forward(rgb)

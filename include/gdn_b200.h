@@ -214,10 +214,10 @@ int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, in
 int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, gdn_stream stream);
 
-/* same, with the two step-dependent scalars read from device memory: dyn[0] = lr / (1 - beta1^t),
- * dyn[1] = 1 / sqrt(1 - beta2^t) -- lets a whole training step live in one captured CUDA graph. */
-int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, const float* dyn, float beta1,
-                      float beta2, float eps, float weight_decay, float grad_scale, gdn_stream stream);
+/* same, with the learning rate and the step counter in device memory: dyn[0] = lr, dyn[1] = number of steps taken so
+ * far (incremented by this call before use) -- lets a whole training step live in one captured CUDA graph. */
+int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, float* dyn, double beta1, double beta2,
+                      float eps, float weight_decay, float grad_scale, gdn_stream stream);
 
 const char* gdn_last_error(void);
 int gdn_version(void);
