@@ -71,9 +71,6 @@ class Engine:
         """params: state_dict-like mapping (no 'module.' prefix) to the module's OWN cuda fp32 tensors
         (parameters are read in place, BN running statistics are updated in place in train mode).
         want: tensor names whose fp32 NHWC value must be available after forward()."""
-        if H % 16 or W % 16:
-            raise ValueError("gdn_b200: height and width must be multiples of 16 (got %dx%d), like the reference "
-                             "networks themselves (SURVEY.md 0.4)" % (H, W))
         self.L = _lib.lib()
         self.g, self.P, self.N, self.H, self.W = graph, params, N, H, W
         self.train, self.do_bwd = train, backward

@@ -115,6 +115,9 @@ def run_network(module, x, istrain):
     _engines(module)
     if x.dim() != 4 or x.shape[1] != graph.cin:
         raise ValueError("gdn_b200: expected input (N, %d, H, W), got %s" % (graph.cin, tuple(x.shape)))
+    if x.shape[2] % 16 or x.shape[3] % 16:
+        raise ValueError("gdn_b200: height and width must be multiples of 16 (got %dx%d), like the reference networks "
+                         "themselves (SURVEY.md 0.4: odd sizes break the skip concatenation)" % (x.shape[2], x.shape[3]))
     named = [(n, p) for n, p in module.named_parameters()]
     needs_grad = module.training and torch.is_grad_enabled() and any(p.requires_grad for _, p in named)
     if needs_grad:

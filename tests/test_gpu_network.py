@@ -222,24 +222,57 @@ def test_train_mode_whole_network_sanity():
     assert int(st["res64_down1.main.1.num_batches_tracked"]) == 1
 
 
-def test_module_autograd_training_loop_decreases_loss():
-    """the drop-in contract: model.train(); loss.backward(); torch optimizer step -- as trainer.py:466-468 does"""
+@pytest.mark.parametrize("name,cin", NETS[:2])
+def test_whole_network_gradient_is_a_descent_direction(name, cin):
+    """End-to-end check of the whole-network backward through the drop-in module API (model.train(); loss.backward()
+    as trainer.py:466-468): a small step against the gradient must lower the loss by about lr*|g|^2 (first-order
+    Taylor), which holds however ill-conditioned the train-mode network is."""
+    from oracle import synth
+    m, _ = _module(name, seed=0)
+    m.train()
+    x = _inputs(cin).to(dev)
+    tgt = synth.synth_depth(B, H, W, 7).to(dev)
+
+    def loss_of():
+        return ((m(x, istrain=False) - tgt) ** 2).mean()
+
+    loss0 = loss_of()
+    m.zero_grad()
+    loss0.backward()
+    params = [p for p in m.parameters()]
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)
+    g2 = sum((p.grad.double() ** 2).sum() for p in params).item()
+    assert g2 > 0
+    lr = 0.05 * loss0.item() / g2              # predicted decrease: 5 % of the loss
+    with torch.no_grad():
+        for p in params:
+            p.add_(p.grad, alpha=-lr)
+        loss1 = loss_of().item()
+    drop = loss0.item() - loss1
+    assert 0.3 * 0.05 * loss0.item() <= drop <= 1.7 * 0.05 * loss0.item(), (loss0.item(), loss1, drop)
+
+
+def test_module_autograd_with_torch_and_fused_optimizers():
+    """the drop-in contract: any torch optimizer works on the parameters' .grad; FusedAdam matches optim.Adam"""
     from oracle import synth
     from gdn_pytorch_b200.ops import FusedAdam
     m, _ = _module("AutoEncoder_DtoD", seed=0)
     m.train()
     dep = synth.synth_depth(B, H, W, 0).to(dev)
-    opt = FusedAdam(m.parameters(), 1e-3, (0.9, 0.999), eps=1e-8, weight_decay=5e-4)
-    losses = []
-    for _ in range(6):
-        out = m(dep, istrain=False)
-        loss = ((out - dep) ** 2).mean()
-        opt.zero_grad()
-        loss.backward()
-        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
-        opt.step()
-        losses.append(loss.item())
-    assert losses[-1] < losses[0]
+    out = m(dep, istrain=False)
+    loss = ((out - dep) ** 2).mean()
+    m.zero_grad()
+    loss.backward()
+    p = m.upconv4.weight
+    g = p.grad.clone()
+    ref = p.detach().clone()
+    from oracle import adam as OA
+    OA.adam_step(ref, g, torch.zeros_like(ref), torch.zeros_like(ref), 1, 1e-4)
+    opt = FusedAdam(m.parameters(), 1e-4, (0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    opt.step()
+    assert torch.allclose(p.detach(), ref, rtol=1e-5, atol=1e-8)
+    out2 = m(dep, istrain=False)               # engines re-pack the updated weights
+    assert not torch.equal(out2, out)
 
 
 def test_rtod_train_step_against_oracle():
