@@ -1,10 +1,13 @@
 // Implicit-GEMM convolution for sm_100a: tcgen05.mma (BF16 x BF16 -> FP32 in TMEM), TMA-staged NHWC tiles.
 //
-// One persistent CTA per SM, 7 warps:
+// One persistent CTA per SM, 8 warps:
 //   warps 0-3  epilogue  (TMEM -> registers -> bias / ReLU / residual / tanh / BN statistics -> global)
 //   warp  4    A producer (activations, TMA)
-//   warp  5    MMA issuer (one elected thread) + TMEM owner
+//   warp  5    MMA issuer 0 (one elected thread) + TMEM owner
 //   warp  6    B producer (weights, TMA)
+//   warp  7    MMA issuer 1: when a tile has J >= 2 sub-tiles the two issuers split them (disjoint accumulators).
+//              One issuer alone is instruction-latency bound (~70 cycles per MMA measured with ncu source
+//              counters against the 48 / 64 cycles an N = 64 / 128 MMA needs), two are not.
 //
 // GEMM view: D[pixels(128), Cout tile(BN)] += A[pixels, 64 ch] * W[tap][Cout tile, 64 ch]^T over taps x 64-ch chunks.
 //
@@ -23,8 +26,8 @@
 
 namespace gdn {
 
-constexpr int kThreads = 7 * 32;
-constexpr int kWarpA = 4, kWarpMMA = 5, kWarpB = 6;
+constexpr int kThreads = 8 * 32;
+constexpr int kWarpA = 4, kWarpMMA = 5, kWarpB = 6, kWarpMMA2 = 7;
 constexpr int kMaxA = 8, kMaxB = 8;
 
 struct ConvK {
@@ -39,6 +42,7 @@ struct ConvK {
   int halo_w;
   uint32_t a_bytes;
   int na, nbst, acc_bufs;
+  int nmma;                  // MMA issuer warps in use (2 when J >= 2)
   const float* bias;
   int relu, tanh_out;
   const float* resid;
@@ -117,14 +121,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxA; i++) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], p.nmma);
     }
     for (int i = 0; i < kMaxB; i++) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], p.nmma);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_full[i], p.nmma);
       mbar_init(&acc_empty[i], 4);
     }
     fence_mbar_init();
@@ -212,60 +216,87 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
       }
     }
-  } else if (warp == kWarpMMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The WHOLE warp runs this (warp-uniform) loop so that descriptors live in uniform registers; one elected
+  } else if (warp == kWarpMMA || warp == kWarpMMA2) {
+    // ------------------------------------------------------------------ MMA issuers
+    // A WHOLE warp runs this (warp-uniform) loop so that descriptors live in uniform registers; one elected
     // lane issues all MMAs of a (tap, chunk) step back to back as "64-bit descriptor base + immediate"
     // (one UIADD3.64 + one UTCHMMA per MMA -- see tools/probe_mma_rate.cu for the issue-rate measurements).
-    Ring ra, rb, rc;
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-    const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
-    const uint64_t a_hi = make_smem_desc_sw128(0, 0, a_sbo);
-    const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    const int J = p.J;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
-      tc_fence_after();
-      const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride);
-      for (int c = 0; c < chunks; c++) {
-        if (halo) mbar_wait(&a_full[ra.i], ra.ph);
-        for (int r = 0; r < p.kh; r++)
-          for (int s = 0; s < p.kw; s++) {
-            if (!halo) mbar_wait(&a_full[ra.i], ra.ph);
-            mbar_wait(&b_full[rb.i], rb.ph);
-            tc_fence_after();
-            const uint32_t a0 = sA_u + (uint32_t)ra.i * p.a_bytes + (halo ? (uint32_t)(r * p.halo_w + s) * 128u : 0u);
-            const uint64_t ad0 = a_hi + (uint64_t)((a0 & 0x3FFFFu) >> 4);
-            const uint64_t bd0 = b_hi + (uint64_t)(((sB_u + (uint32_t)rb.i * B_BYTES) & 0x3FFFFu) >> 4);
-            const uint32_t first = (c == 0 && r == 0 && s == 0) ? 0u : 1u;
-            if (elect_one()) {
-              // sub-tile j is 8 pixels (1024 B) further along the halo row; K advances 32 B per 16-channel step
+    // Issuer `who` owns sub-tiles [j0, j1) of every tile; every issuer waits on the same full barriers and
+    // commits to the same empty barriers (their arrival count is the number of issuers).
+    const int who = (warp == kWarpMMA) ? 0 : 1;
+    if (who < p.nmma) {
+      Ring ra, rb, rc;
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
+      const uint64_t a_hi = make_smem_desc_sw128(0, 0, a_sbo);
+      const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      const int jn = p.J / p.nmma;                 // sub-tiles per issuer (1 or 2; J itself when alone)
+      const int j0 = who * jn;
+      const uint32_t a_j0 = (uint32_t)(j0 * 64);   // descriptor units (16 B): sub-tile j is 1024 B along the halo row
+      const uint32_t acc_j0 = (uint32_t)(j0 * BN);
+      const int kh = p.kh, kw = p.kw, na = p.na, nbst = p.nbst;
+      const uint32_t a_bytes = p.a_bytes;
+      const uint32_t row_skip = halo ? (uint32_t)(p.halo_w - kw) * 128u : 0u;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
+        tc_fence_after();
+        const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride) + acc_j0;
+        uint32_t accum = 0u;
+        for (int c = 0; c < chunks; c++) {
+          if (halo) mbar_wait(&a_full[ra.i], ra.ph);
+          uint32_t a_off = sA_u + (uint32_t)ra.i * a_bytes;   // halo: shifted window start, advanced tap by tap
+          for (int r = 0; r < kh; r++) {
+            for (int s = 0; s < kw; s++) {
+              if (!halo) {
+                mbar_wait(&a_full[ra.i], ra.ph);
+                a_off = sA_u + (uint32_t)ra.i * a_bytes;
+              }
+              mbar_wait(&b_full[rb.i], rb.ph);
+              tc_fence_after();
+              const uint64_t ad0 = a_hi + (uint64_t)(((a_off & 0x3FFFFu) >> 4) + a_j0);
+              const uint64_t bd0 = b_hi + (uint64_t)(((sB_u + (uint32_t)rb.i * B_BYTES) & 0x3FFFFu) >> 4);
+              if (elect_one()) {
+                if (jn == 4) {
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                if (j < J) {
+                  for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)
+                      umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
+                                idesc, k4 ? 1u : accum);
+                } else if (jn == 2) {
+#pragma unroll
+                  for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)
+                      umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
+                                idesc, k4 ? 1u : accum);
+                } else {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; k4++)
-                    umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
-                              idesc, first | (uint32_t)k4);
+                    umma_bf16(acc_addr, ad0 + (uint64_t)(k4 * 2), bd0 + (uint64_t)(k4 * 2), idesc, k4 ? 1u : accum);
                 }
+                umma_commit(&b_empty[rb.i]);
+                if (!halo) umma_commit(&a_empty[ra.i]);
               }
-              umma_commit(&b_empty[rb.i]);
-              if (!halo) umma_commit(&a_empty[ra.i]);
+              __syncwarp();
+              accum = 1u;
+              rb.next(nbst);
+              if (!halo) ra.next(na);
+              a_off += 128u;
             }
-            __syncwarp();
-            rb.next(p.nbst);
-            if (!halo) ra.next(p.na);
+            a_off += row_skip;
           }
-        if (halo) {
-          if (elect_one()) umma_commit(&a_empty[ra.i]);
-          __syncwarp();
-          ra.next(p.na);
+          if (halo) {
+            if (elect_one()) umma_commit(&a_empty[ra.i]);
+            __syncwarp();
+            ra.next(na);
+          }
         }
+        if (elect_one()) umma_commit(&acc_full[rc.i]);
+        __syncwarp();
+        rc.next(p.acc_bufs);
       }
-      if (elect_one()) umma_commit(&acc_full[rc.i]);
-      __syncwarp();
-      rc.next(p.acc_bufs);
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps 0..3
@@ -530,7 +561,8 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   if (d->out_reflect && d->out_bf16.ptr && (d->out_bf16.pad >= d->dst_h || d->out_bf16.pad >= d->dst_w))
     return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: reflection border %d >= extent", d->out_bf16.pad);
 
-  int mode = d->algo;
+  int mode = d->algo & 0xff;
+  const int j_req = (d->algo >> 8) & 0xff;  // HALO: sub-tiles per tile requested by the caller's autotuner (0 = heuristic)
   const int taps = d->kh * d->kw;
   if (mode == GDN_CONV_AUTO)
     mode = (d->stride == 1 && !two && taps > 1 && d->out_h >= 16 && d->out_w >= 16) ? GDN_CONV_HALO : GDN_CONV_TAPBOX;
@@ -543,10 +575,16 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   int rc;
   if (mode == GDN_CONV_HALO) {
     int J = BN <= 64 ? 4 : 2;
-    // halve J while a quarter or more of the computed columns would fall outside the image
-    while (J > 1) {
-      const int cols = (d->out_w + 8 * J - 1) / (8 * J) * (8 * J);
-      if ((cols - d->out_w) * 4 >= cols) J /= 2; else break;
+    if (j_req) {
+      if ((j_req != 1 && j_req != 2 && j_req != 4) || j_req * BN > 512)
+        return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: %d sub-tiles of %d channels do not fit tensor memory", j_req, BN);
+      J = j_req;
+    } else {
+      // halve J while a quarter or more of the computed columns would fall outside the image
+      while (J > 1) {
+        const int cols = (d->out_w + 8 * J - 1) / (8 * J) * (8 * J);
+        if ((cols - d->out_w) * 4 >= cols) J /= 2; else break;
+      }
     }
     const int halo_h = 16 + d->kh - 1;
     int halo_w = 8 * J + d->kw - 1;
@@ -560,6 +598,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     if (k.nbst > kMaxB) k.nbst = kMaxB;
     if (k.nbst < 2) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: halo tile does not fit shared memory");
     k.acc_bufs = (2 * J * BN <= 512) ? 2 : 1;
+    k.nmma = J >= 2 ? 2 : 1;
     k.tiles_x = (d->out_w + 8 * J - 1) / (8 * J);
     k.tiles_y = (d->out_h + 15) / 16;
     k.nb = 1;
@@ -578,6 +617,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     k.th_log2 = ilog2(th);
     k.nb = nb;
     k.a_bytes = 128 * 128;
+    k.nmma = 1;
     k.acc_bufs = (2 * BN <= 512) ? 2 : 1;
     size_t per = k.a_bytes + b_bytes;
     int st = (int)(smem_budget / per);

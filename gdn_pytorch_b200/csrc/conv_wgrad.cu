@@ -19,8 +19,8 @@
 
 namespace gdn {
 
-constexpr int kWgThreads = 7 * 32;
-constexpr int kWgWarpX = 4, kWgWarpMMA = 5, kWgWarpY = 6;
+constexpr int kWgThreads = 8 * 32;
+constexpr int kWgWarpX = 4, kWgWarpMMA = 5, kWgWarpY = 6, kWgWarpMMA2 = 7;  // two MMA issuers split the units (even / odd)
 constexpr int kMaxUnits = 64;
 constexpr int kWgStagesMax = 8;
 
@@ -78,11 +78,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStagesMax; i++) {
       mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], 1);
+      mbar_init(&x_empty[i], halo ? 2 : 1);   // HALO: both issuers read every X stage; TAPBOX: a stage belongs to one unit
       mbar_init(&y_full[i], 1);
-      mbar_init(&y_empty[i], 1);
+      mbar_init(&y_empty[i], 2);
     }
-    mbar_init(&acc_full, 1);
+    mbar_init(&acc_full, 2);
     mbar_init(&acc_empty, 4);
     fence_mbar_init();
   }
@@ -193,8 +193,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
         }
       }
     }
-  } else if (warp == kWgWarpMMA) {
-    // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+  } else if (warp == kWgWarpMMA || warp == kWgWarpMMA2) {
+    // ------------------------------------------------------------ MMA issuers (whole warp, elected lane issues)
+    // Issuer `who` takes units u0 + who, u0 + who + 2, ...; both wait on the same full barriers and commit to the
+    // same empty barriers (arrival count 2), except TAPBOX X stages, which belong to exactly one unit.
+    const int who = (warp == kWgWarpMMA) ? 0 : 1;
     WRing rx, ry;
     uint32_t accph = 0;
     constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
@@ -220,7 +223,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           mbar_wait(&x_full[rx.i], rx.ph);
           tc_fence_after();
           const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
-          for (int u = u0; u < u1; u++) {
+          for (int u = u0 + who; u < u1; u += 2) {
             const WgUnit un = p.units[u];
             const uint32_t a0 = xb + (uint32_t)(un.rA * p.halo_w + un.sA) * 128u;
             const uint32_t lbo = un.sB < 0 ? 128u : (uint32_t)((un.rB - un.rA) * p.halo_w + (un.sB - un.sA)) * 128u;
@@ -244,18 +247,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           rx.next(p.nstage);
         } else {
           for (int u = u0; u < u1; u++) {
-            mbar_wait(&x_full[rx.i], rx.ph);
-            tc_fence_after();
-            const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
-            const uint64_t ad0 = a_hi_tap + (uint64_t)((xb & 0x3FFFFu) >> 4);
-            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
-            if (elect_one()) {
+            if (((u - u0) & 1) == who) {
+              mbar_wait(&x_full[rx.i], rx.ph);
+              tc_fence_after();
+              const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
+              const uint64_t ad0 = a_hi_tap + (uint64_t)((xb & 0x3FFFFu) >> 4);
+              const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
+              if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ks++)
-                umma_bf16(acc, ad0 + (uint64_t)(ks * 128), bd0 + (uint64_t)(ks * 128), idesc, first_t | (uint32_t)ks);
-              umma_commit(&x_empty[rx.i]);
+                for (int ks = 0; ks < 8; ks++)
+                  umma_bf16(acc, ad0 + (uint64_t)(ks * 128), bd0 + (uint64_t)(ks * 128), idesc, first_t | (uint32_t)ks);
+                umma_commit(&x_empty[rx.i]);
+              }
+              __syncwarp();
             }
-            __syncwarp();
             rx.next(p.nstage);
           }
         }

@@ -19,6 +19,18 @@ static inline int ew_grid(long long work) {
   return (int)b;
 }
 
+static inline int ew_lg2(int v) {  // log2 of a power of two, -1 otherwise
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < v) l++;
+  return l;
+}
+
+static inline int ew_row_grid(long long rows) {
+  const long long cap = (long long)device_sm_count() * 8;
+  return (int)(rows < cap ? (rows < 1 ? 1 : rows) : cap);
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   // nn.ReflectionPad2d index map (no edge repeat); valid for |overshoot| < n
   if (i < 0) i = -i;
@@ -89,6 +101,55 @@ __global__ void im2col_kernel(const float* __restrict__ src, __nv_bfloat16* __re
       f[j] = v;
     }
     *reinterpret_cast<uint4*>(dst + pix * kpad + g * 8) = pack8(f);
+  }
+}
+
+
+// fast path: one image row per CTA iteration; the (r, s, c) decomposition of every column lives in a shared-memory
+// table, all index math is 32-bit.
+__global__ void __launch_bounds__(kEwThreads) im2col_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                 int N, int C, int H, int W, int kh, int kw, int pad,
+                                                                 int reflect, int kpad) {
+  extern __shared__ int s_tab[];  // [kpad]: r | s << 8 | c << 16, or -1 beyond kh*kw*C
+  const int kreal = kh * kw * C;
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    int e = -1;
+    if (k < kreal) {
+      const int c = k % C, t = k / C;
+      e = (t / kw) | ((t % kw) << 8) | (c << 16);
+    }
+    s_tab[k] = e;
+  }
+  __syncthreads();
+  const int groups = kpad >> 3;
+  const int items = W * groups;
+  const int rows = N * H;
+  const int plane = H * W;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, y = row - n * H;
+    const float* img = src + (size_t)n * C * plane;
+    for (int it = threadIdx.x; it < items; it += kEwThreads) {
+      const int x = it / groups, g = it - x * groups;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int e = s_tab[g * 8 + j];
+        float v = 0.f;
+        if (e >= 0) {
+          int yy = y + (e & 255) - pad, xx = x + ((e >> 8) & 255) - pad;
+          bool ok = true;
+          if (reflect) {
+            yy = reflect_idx(yy, H);
+            xx = reflect_idx(xx, W);
+          } else {
+            ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+          }
+          if (ok) v = __ldg(img + (e >> 16) * plane + yy * W + xx);
+        }
+        f[j] = v;
+      }
+      *reinterpret_cast<uint4*>(dst + ((size_t)row * W + x) * kpad + g * 8) = pack8(f);
+    }
   }
 }
 
@@ -243,6 +304,174 @@ __global__ void act_forward_kernel(const ActFwd a) {
   }
 }
 
+
+// ---- fast paths (the ones the networks use): one image row per CTA iteration, 32-bit index math (channel-group
+// counts are powers of two), two independent items in flight per thread.  The generic kernel above stays as the
+// path for everything else (align_corners=True upsampling, odd channel counts).
+__device__ __forceinline__ void act_finish8(const ActFwd& a, float* v, const float* sc, const float* sh,
+                                            const float4& r0, const float4& r1) {
+  if (a.scale) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], sc[j], sh[j]);
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.resid) {
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+  }
+}
+
+// source-driven: every source pixel is read once and written to out_f32 and to the interior + reflection images of
+// out_bf16 (no upsampling / dilation).
+__global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  const int cgm = (1 << lg_cg) - 1;
+  const int items = a.W << lg_cg;
+  const int c8 = (threadIdx.x & cgm) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = a.scale ? a.scale[c8 + j] : 1.f;
+    sh[j] = a.scale ? a.shift[c8 + j] : 0.f;
+  }
+  const int P = a.P, Hp = a.H + 2 * P, Wp = a.W + 2 * P;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / a.H, y = row - n * a.H;
+    int ys[3], ny = 0;
+    ys[ny++] = y + P;
+    if (a.reflect && a.out_bf16) {
+      if (y >= 1 && y <= P) ys[ny++] = P - y;
+      if (y >= a.H - 1 - P && y <= a.H - 2) ys[ny++] = P + 2 * (a.H - 1) - y;
+    }
+    const size_t row_off = (size_t)row * a.W * a.C;
+    for (int it0 = threadIdx.x; it0 < items; it0 += 2 * kEwThreads) {
+      float v[2][8];
+      float4 r0[2], r1[2];
+      bool live[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int it = it0 + u * kEwThreads;
+        live[u] = it < items;
+        if (!live[u]) continue;
+        const size_t off = row_off + (size_t)(it >> lg_cg) * a.C + c8;
+        if (a.src_bf16) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + off));
+          if (a.src_half) unpack8h(q, v[u]); else unpack8(q, v[u]);
+        } else {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + off));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + off + 4));
+          v[u][0] = p0.x; v[u][1] = p0.y; v[u][2] = p0.z; v[u][3] = p0.w;
+          v[u][4] = p1.x; v[u][5] = p1.y; v[u][6] = p1.z; v[u][7] = p1.w;
+        }
+        if (a.resid) {
+          r0[u] = __ldg(reinterpret_cast<const float4*>(a.resid + off));
+          r1[u] = __ldg(reinterpret_cast<const float4*>(a.resid + off + 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (!live[u]) continue;
+        const int x = (it0 + u * kEwThreads) >> lg_cg;
+        act_finish8(a, v[u], sc, sh, r0[u], r1[u]);
+        if (a.out_f32) {
+          float* o = a.out_f32 + row_off + (size_t)x * a.C + c8;
+          *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+        }
+        if (a.out_bf16) {
+          const uint4 w = pack8(v[u]);
+          int xs[3], nx = 0;
+          xs[nx++] = x + P;
+          if (a.reflect) {
+            if (x >= 1 && x <= P) xs[nx++] = P - x;
+            if (x >= a.W - 1 - P && x <= a.W - 2) xs[nx++] = P + 2 * (a.W - 1) - x;
+          }
+          for (int p = 0; p < ny; p++)
+            for (int q = 0; q < nx; q++)
+              *reinterpret_cast<uint4*>(a.out_bf16 + (((size_t)n * Hp + ys[p]) * Wp + xs[q]) * a.C + c8) = w;
+        }
+      }
+    }
+  }
+}
+
+// output-driven x2 bilinear upsampling (align_corners=False) with an optional reflection border: one padded output
+// row per CTA iteration; the row's two source rows and the vertical weight are computed once per row.
+__global__ void __launch_bounds__(kEwThreads) act_up_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  const int cgm = (1 << lg_cg) - 1;
+  const int OH = 2 * a.H, OW = 2 * a.W;
+  const int P = a.P, Hp = OH + 2 * P, Wp = OW + 2 * P;
+  const int items = Wp << lg_cg;
+  const int c8 = (threadIdx.x & cgm) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = a.scale ? a.scale[c8 + j] : 1.f;
+    sh[j] = a.scale ? a.shift[c8 + j] : 0.f;
+  }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Hp, yp = row - n * Hp;
+    int Y = yp - P;
+    if ((Y < 0 || Y >= OH) && !a.reflect) continue;
+    Y = reflect_idx(Y, OH);
+    int y0, y1;
+    float wy;
+    up_coord(Y, a.H, 1, y0, y1, wy);
+    const size_t base0 = ((size_t)n * a.H + y0) * a.W, base1 = ((size_t)n * a.H + y1) * a.W;
+    for (int it = threadIdx.x; it < items; it += kEwThreads) {
+      const int xp = it >> lg_cg;
+      int X = xp - P;
+      if ((X < 0 || X >= OW) && !a.reflect) continue;
+      X = reflect_idx(X, OW);
+      int x0, x1;
+      float wx;
+      up_coord(X, a.W, 1, x0, x1, wx);
+      float v00[8], v01[8], v10[8], v11[8];
+      const size_t o00 = (base0 + x0) * a.C + c8, o01 = (base0 + x1) * a.C + c8;
+      const size_t o10 = (base1 + x0) * a.C + c8, o11 = (base1 + x1) * a.C + c8;
+      if (a.src_bf16) {
+        const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + o00));
+        const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + o01));
+        const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + o10));
+        const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + o11));
+        if (a.src_half) { unpack8h(q00, v00); unpack8h(q01, v01); unpack8h(q10, v10); unpack8h(q11, v11); }
+        else { unpack8(q00, v00); unpack8(q01, v01); unpack8(q10, v10); unpack8(q11, v11); }
+      } else {
+        const size_t os[4] = {o00, o01, o10, o11};
+        float* vs[4] = {v00, v01, v10, v11};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + os[k]));
+          const float4 p1 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + os[k] + 4));
+          vs[k][0] = p0.x; vs[k][1] = p0.y; vs[k][2] = p0.z; vs[k][3] = p0.w;
+          vs[k][4] = p1.x; vs[k][5] = p1.y; vs[k][6] = p1.z; vs[k][7] = p1.w;
+        }
+      }
+      float4 r00[2] = {z4, z4}, r01[2] = {z4, z4}, r10[2] = {z4, z4}, r11[2] = {z4, z4};
+      if (a.resid) {
+        r00[0] = __ldg(reinterpret_cast<const float4*>(a.resid + o00)); r00[1] = __ldg(reinterpret_cast<const float4*>(a.resid + o00 + 4));
+        r01[0] = __ldg(reinterpret_cast<const float4*>(a.resid + o01)); r01[1] = __ldg(reinterpret_cast<const float4*>(a.resid + o01 + 4));
+        r10[0] = __ldg(reinterpret_cast<const float4*>(a.resid + o10)); r10[1] = __ldg(reinterpret_cast<const float4*>(a.resid + o10 + 4));
+        r11[0] = __ldg(reinterpret_cast<const float4*>(a.resid + o11)); r11[1] = __ldg(reinterpret_cast<const float4*>(a.resid + o11 + 4));
+      }
+      act_finish8(a, v00, sc, sh, r00[0], r00[1]);
+      act_finish8(a, v01, sc, sh, r01[0], r01[1]);
+      act_finish8(a, v10, sc, sh, r10[0], r10[1]);
+      act_finish8(a, v11, sc, sh, r11[0], r11[1]);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float top = (1.f - wx) * v00[j] + wx * v01[j];
+        const float bot = (1.f - wx) * v10[j] + wx * v11[j];
+        v[j] = (1.f - wy) * top + wy * bot;
+      }
+      *reinterpret_cast<uint4*>(a.out_bf16 + ((size_t)row * Wp + xp) * a.C + c8) = pack8(v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ BN backward
 struct BnBwd {
   const float* dact;              // fp32 [N][H][W][C] gradient w.r.t. the activation output
@@ -371,6 +600,109 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
   }
 }
 
+
+// ---- fast paths: contiguous pixel ranges per CTA, 32-bit index math, two items in flight per thread
+__device__ __forceinline__ void bn_load8(const BnBwd& b, size_t off, float* x, float* d) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(b.raw + off));
+  const float4 d0 = __ldg(reinterpret_cast<const float4*>(b.dact + off));
+  const float4 d1 = __ldg(reinterpret_cast<const float4*>(b.dact + off + 4));
+  if (b.raw_half) unpack8h(q, x); else unpack8(q, x);
+  d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+}
+
+// per-channel sums of g and g*(x - mean) (scaled by rstd at the end); items = npix * cg, block-contiguous chunks
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const BnBwd b, const int lg_cg, const int chunk) {
+  extern __shared__ float s_red[];  // [2][C]
+  const int cgm = (1 << lg_cg) - 1;
+  const int c8 = (threadIdx.x & cgm) * 8;
+  for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  // sx accumulates g*x; the mean is taken out once per thread at the end (sum g*(x - mu) = sum g*x - mu * sum g)
+  float sc[8], sh[8], sg[8], sx[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = b.scale[c8 + j];
+    sh[j] = b.shift[c8 + j];
+    sg[j] = sx[j] = 0.f;
+  }
+  const long long total = b.npix << lg_cg;
+  const long long i0 = (long long)blockIdx.x * chunk;
+  const long long i1 = (i0 + chunk < total) ? i0 + chunk : total;
+  for (long long it0 = i0 + threadIdx.x; it0 < i1; it0 += 2 * kEwThreads) {
+    float x[2][8], d[2][8];
+    const bool two = it0 + kEwThreads < i1;
+    bn_load8(b, (size_t)it0 * 8, x[0], d[0]);
+    if (two) bn_load8(b, (size_t)(it0 + kEwThreads) * 8, x[1], d[1]);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (u == 1 && !two) break;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float gq = d[u][j];
+        if (b.relu && fmaf(x[u][j], sc[j], sh[j]) <= 0.f) gq = 0.f;
+        sg[j] += gq;
+        sx[j] = fmaf(gq, x[u][j], sx[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    atomicAdd(&s_red[c8 + j], sg[j]);
+    atomicAdd(&s_red[b.C + c8 + j], (sx[j] - b.mean[c8 + j] * sg[j]) * b.rstd[c8 + j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < b.C; i += blockDim.x) {
+    atomicAdd(b.sum_g + i, (double)s_red[i]);
+    atomicAdd(b.sum_gx + i, (double)s_red[b.C + i]);
+  }
+}
+
+// dy = scale * (g - mean(g) - xhat * mean(g xhat)), no dilation: flat item index == flat element index / 8
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const BnBwd b, const int lg_cg, const int chunk) {
+  const int cgm = (1 << lg_cg) - 1;
+  const int c8 = (threadIdx.x & cgm) * 8;
+  const double inv_n = 1.0 / (double)b.npix;
+  if (b.dgamma && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
+      b.dgamma[c] += (float)(b.sum_gx[c]);
+      b.dbeta[c] += (float)(b.sum_g[c]);
+    }
+  }
+  // dy = sc*(g - m1 - (x - mu)*rs*m2) = sc*g + k1*x + k0
+  float sc[8], sh[8], k1[8], k0[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = b.scale[c8 + j];
+    sh[j] = b.shift[c8 + j];
+    const float m1 = (float)(b.sum_g[c8 + j] * inv_n);
+    const float m2 = (float)(b.sum_gx[c8 + j] * inv_n);
+    const float t = sc[j] * b.rstd[c8 + j] * m2;
+    k1[j] = -t;
+    k0[j] = t * b.mean[c8 + j] - sc[j] * m1;
+  }
+  const long long total = b.npix << lg_cg;
+  const long long i0 = (long long)blockIdx.x * chunk;
+  const long long i1 = (i0 + chunk < total) ? i0 + chunk : total;
+  for (long long it0 = i0 + threadIdx.x; it0 < i1; it0 += 2 * kEwThreads) {
+    float x[2][8], d[2][8];
+    const bool two = it0 + kEwThreads < i1;
+    bn_load8(b, (size_t)it0 * 8, x[0], d[0]);
+    if (two) bn_load8(b, (size_t)(it0 + kEwThreads) * 8, x[1], d[1]);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (u == 1 && !two) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float gq = d[u][j];
+        if (b.relu && fmaf(x[u][j], sc[j], sh[j]) <= 0.f) gq = 0.f;
+        o[j] = fmaf(sc[j], gq, fmaf(k1[j], x[u][j], k0[j]));
+      }
+      *reinterpret_cast<uint4*>(b.dy + (size_t)(it0 + u * kEwThreads) * 8) = pack8(o);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------- fold grad
 struct FoldK {
   const float* dpad;   // fp32 [N][OH+2P][OW+2P][ctot]: gradient w.r.t. the conv's input buffer
@@ -452,6 +784,97 @@ __global__ void fold_grad_kernel(const FoldK f) {
   }
 }
 
+
+// fast path: one source row (n, y) per CTA iteration; the hi-res rows feeding it (and their reflection images) are
+// found once per row (shared memory), the columns per thread in registers (fully unrolled candidate x mirror grid),
+// 32-bit index math, 4 channels (16 B) per thread item.
+__global__ void __launch_bounds__(kEwThreads) fold_rows_kernel(const FoldK f, const int lg_cg, const int rows) {
+  __shared__ int s_prow[12];
+  __shared__ float s_pw[12];
+  __shared__ int s_np;
+  const int cgm = (1 << lg_cg) - 1;
+  const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
+  const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
+  const int items = f.W << lg_cg;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / f.H, y = row - n * f.H;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int np = 0;
+      const int ylo = f.up ? 2 * y - 1 : (f.dilate ? 2 * y : y), yhi = f.up ? 2 * y + 2 : ylo;
+      for (int Y = ylo; Y <= yhi; Y++) {
+        if (Y < 0 || Y >= OH) continue;
+        float w = 1.f;
+        if (f.up) {
+          int a0, a1;
+          float w1;
+          up_coord(Y, f.H, f.up, a0, a1, w1);
+          w = (a0 == y ? 1.f - w1 : 0.f) + (a1 == y ? w1 : 0.f);
+          if (w == 0.f) continue;
+        }
+        int my[3];
+        const int cy = mirror_set(Y, OH, f.P, f.reflect, my);
+        for (int p = 0; p < cy; p++) { s_prow[np] = my[p]; s_pw[np++] = w; }
+      }
+      s_np = np;
+    }
+    __syncthreads();
+    const int np = s_np;
+    const size_t img = (size_t)n * Hq;
+    for (int it = threadIdx.x; it < items; it += kEwThreads) {
+      const int x = it >> lg_cg, c4 = (it & cgm) * 4;
+      // candidate hi-res columns (4 when upsampling, else 1) x up to 3 reflection images; -1 = unused
+      int pcol[4][3];
+      float qw[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        qw[k] = 0.f;
+        pcol[k][0] = pcol[k][1] = pcol[k][2] = -1;
+        int X;
+        if (f.up) X = 2 * x - 1 + k;
+        else if (k == 0) X = f.dilate ? 2 * x : x;
+        else continue;
+        if (X < 0 || X >= OW) continue;
+        float w = 1.f;
+        if (f.up) {
+          int a0, a1;
+          float w1;
+          up_coord(X, f.W, f.up, a0, a1, w1);
+          w = (a0 == x ? 1.f - w1 : 0.f) + (a1 == x ? w1 : 0.f);
+          if (w == 0.f) continue;
+        }
+        qw[k] = w;
+        pcol[k][0] = X + f.P;
+        if (f.reflect) {
+          if (X >= 1 && X <= f.P) pcol[k][1] = f.P - X;
+          if (X >= OW - 1 - f.P && X <= OW - 2) pcol[k][2] = f.P + 2 * (OW - 1) - X;
+        }
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < np; p++) {
+        const float* rowp = f.dpad + ((img + s_prow[p]) * Wq) * f.ctot + f.c_off + c4;
+        const float wr = s_pw[p];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            if (pcol[k][m] < 0) continue;
+            const float w = wr * qw[k];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + (size_t)pcol[k][m] * f.ctot));
+            acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+          }
+        }
+      }
+      float* o = f.dact + ((size_t)row * f.W + x) * f.C + c4;
+      if (f.accumulate) {
+        const float4 v = *reinterpret_cast<const float4*>(o);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------- weight pack / unpack
 // packed[t][a][b] (t = r*kw + s, a < A, b < B) <-> w[a*sa + b*sb + r'*sr + s'*ss], (r', s') flipped when flip.
 // For im2col'd layers (col_c > 0): packed[0][a][k], k = (r*kw + s)*col_c + c  <->  w[a*sa + c*sb + r*sr + s*ss].
@@ -514,6 +937,79 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
   }
 }
 
+
+// fast paths for ordinary (non-im2col) layers whose taps are contiguous in the parameter tensor (stride_s == 1,
+// stride_r == kw): a CTA moves a 16(a) x 16(b) tile for ALL taps through shared memory so that both the fp32
+// parameter side (runs of kh*kw floats per (a, b)) and the packed side (b or a fastest) are accessed in full sectors.
+constexpr int kPackTile = 16;
+constexpr int kPackMaxTaps = 81;
+
+__global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
+                                                       __nv_bfloat16* __restrict__ out, const PackK k) {
+  // tile[a_local][b_local][tap]; parameter address of (a, b, tap) = a*sa + b*sb + tap  (one of sa / sb is T = taps)
+  extern __shared__ float s_tile[];
+  const int T = k.kh * k.kw;
+  const int a0 = blockIdx.y * kPackTile, b0 = blockIdx.x * kPackTile;
+  const bool b_inner = (k.sb == T);  // [a][b][taps] (Conv2d)  vs  [b][a][taps] (ConvTranspose2d / dgrad views)
+  const int run = kPackTile * T;     // contiguous floats per outer index
+  for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
+    const int outer = i / run, rem = i - outer * run;
+    const int inner = rem / T, tap = rem - inner * T;
+    const int al = b_inner ? outer : inner, bl = b_inner ? inner : outer;
+    const int a = a0 + al, b = b0 + bl;
+    float v = 0.f;
+    if (a < k.A && b < k.B) v = __ldg(w + (long long)a * k.sa + (long long)b * k.sb + tap);
+    s_tile[(al * kPackTile + bl) * (T + 1) + tap] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * kPackTile * kPackTile; i += blockDim.x) {
+    const int bl = i & (kPackTile - 1), al = (i >> 4) & (kPackTile - 1), t = i >> 8;
+    const int a = a0 + al, b = b0 + bl;
+    if (a >= k.Apad || b >= k.Bpad) continue;
+    const int tap = k.flip ? T - 1 - t : t;
+    float v = s_tile[(al * kPackTile + bl) * (T + 1) + tap];
+    if (scale_a && a < k.A) v *= scale_a[a];
+    out[((long long)t * k.Apad + a) * k.Bpad + b] = __float2bfloat16(v);
+  }
+}
+
+// grad[a*sa + b*sb + tap] (+)= dw[t][b][a]
+__global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k,
+                                                         int accumulate) {
+  extern __shared__ float s_tile[];
+  const int T = k.kh * k.kw;
+  const int a0 = blockIdx.y * kPackTile, b0 = blockIdx.x * kPackTile;
+  for (int i = threadIdx.x; i < T * kPackTile * kPackTile; i += blockDim.x) {
+    const int al = i & (kPackTile - 1), bl = (i >> 4) & (kPackTile - 1), t = i >> 8;
+    const int a = a0 + al, b = b0 + bl;
+    float v = 0.f;
+    if (a < k.A && b < k.B) v = __ldg(dw + ((long long)t * k.Bpad + b) * k.Apad + a);
+    const int tap = k.flip ? T - 1 - t : t;
+    s_tile[(al * kPackTile + bl) * (T + 1) + tap] = v;
+  }
+  __syncthreads();
+  const bool b_inner = (k.sb == T);
+  const int run = kPackTile * T;
+  for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
+    const int outer = i / run, rem = i - outer * run;
+    const int inner = rem / T, tap = rem - inner * T;
+    const int al = b_inner ? outer : inner, bl = b_inner ? inner : outer;
+    const int a = a0 + al, b = b0 + bl;
+    if (a >= k.A || b >= k.B) continue;
+    float* g = grad + (long long)a * k.sa + (long long)b * k.sb + tap;
+    const float v = s_tile[(al * kPackTile + bl) * (T + 1) + tap];
+    if (accumulate) *g += v; else *g = v;
+  }
+}
+
+static bool pack_tileable(const PackK& k) {
+  const int T = k.kh * k.kw;
+  if (k.col_c || T > kPackMaxTaps) return false;
+  if (!(k.ss == 1 && (k.sr == k.kw || k.kh == 1))) return false;
+  // the inner index must be contiguous runs of T floats: [a][b][T] with sa >= B*T, or [b][a][T] with sb >= A*T
+  return (k.sb == T && k.sa >= (long long)k.B * T) || (k.sa == T && k.sb >= (long long)k.A * T);
+}
+
 // eval-mode BatchNorm folded into a per-channel scale / bias
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
@@ -535,6 +1031,12 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
   if (!src || !dst || c < 1 || c > 4 || kpad % 64 || kh * kw * c > kpad)
     return fail(GDN_INVALID_DESC, "gdn_im2col: bad arguments (c=%d kpad=%d)", c, kpad);
   if (reflect && (pad >= h || pad >= w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_im2col: reflection pad %d >= extent", pad);
+  if (kh < 256 && kw < 256 && (long long)h * w * c < (1ll << 31)) {
+    im2col_rows_kernel<<<ew_row_grid((long long)n * h), kEwThreads, kpad * sizeof(int), (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad);
+    GDN_LAUNCH_CHECK("im2col_rows_kernel");
+    return GDN_OK;
+  }
   const long long work = (long long)n * h * w * (kpad / 8);
   im2col_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad,
                                                                       reflect, kpad);
@@ -583,6 +1085,23 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
   const long long w2 = a.out_bf16 ? (long long)a.N * (OH + 2 * a.P) * (OW + 2 * a.P) * (a.C / 8) : 0;
   const long long work = w1 > w2 ? w1 : w2;
   if (work == 0) return GDN_OK;
+  const int lg = ew_lg2(a.C / 8);
+  const bool small_idx = (long long)a.W * (a.C / 8) * 4 < (1ll << 30) && (long long)a.N * (OH + 2 * a.P) < (1ll << 30);
+  if (lg >= 0 && small_idx && !a.dilate && (a.up == 0 || a.up == 1)) {
+    ActFwd lo = a;
+    if (a.up) lo.out_bf16 = nullptr;
+    if (lo.out_f32 || lo.out_bf16) {
+      const int rows = a.N * a.H;
+      act_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
+      GDN_LAUNCH_CHECK("act_rows_kernel");
+    }
+    if (a.up && a.out_bf16) {
+      const int rows = a.N * (OH + 2 * a.P);
+      act_up_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
+      GDN_LAUNCH_CHECK("act_up_rows_kernel");
+    }
+    return GDN_OK;
+  }
   act_forward_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(a);
   GDN_LAUNCH_CHECK("act_forward_kernel");
   return GDN_OK;
@@ -610,6 +1129,21 @@ GDN_API int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream) {
   BnBwd b{};
   int rc = fill_bnbwd(d, b);
   if (rc) return rc;
+  {
+    const int lg = ew_lg2(b.C / 8);
+    const long long total = b.npix * (b.C / 8);
+    if (lg >= 0 && total < (1ll << 40)) {
+      const long long want = (long long)device_sm_count() * 6;
+      long long chunk = (total + want - 1) / want;
+      chunk = (chunk + 2 * kEwThreads - 1) / (2 * kEwThreads) * (2 * kEwThreads);
+      if (chunk < (1ll << 30)) {
+        const int grid = (int)((total + chunk - 1) / chunk);
+        bn_bwd_reduce_fast_kernel<<<grid, kEwThreads, 2 * b.C * sizeof(float), (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        GDN_LAUNCH_CHECK("bn_bwd_reduce_fast_kernel");
+        return GDN_OK;
+      }
+    }
+  }
   const int lanes = kEwThreads / (b.C / 8);
   long long blocks = (b.npix + lanes - 1) / lanes;
   const long long cap = (long long)device_sm_count() * 4;
@@ -624,6 +1158,21 @@ GDN_API int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream) {
   int rc = fill_bnbwd(d, b);
   if (rc) return rc;
   if (!b.dy) return fail(GDN_INVALID_DESC, "gdn_act_backward: dy is NULL");
+  if (!b.dilate) {
+    const int lg = ew_lg2(b.C / 8);
+    const long long total = b.npix * (b.C / 8);
+    if (lg >= 0) {
+      const long long want = (long long)device_sm_count() * 8;
+      long long chunk = (total + want - 1) / want;
+      chunk = (chunk + 2 * kEwThreads - 1) / (2 * kEwThreads) * (2 * kEwThreads);
+      if (chunk < (1ll << 30)) {
+        const int grid = (int)((total + chunk - 1) / chunk);
+        bn_bwd_apply_fast_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        GDN_LAUNCH_CHECK("bn_bwd_apply_fast_kernel");
+        return GDN_OK;
+      }
+    }
+  }
   const long long work = b.npix * (b.dilate ? 4 : 1) * (b.C / 8);
   bn_bwd_apply_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(b);
   GDN_LAUNCH_CHECK("bn_bwd_apply_kernel");
@@ -639,6 +1188,15 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
   f.N = d->n; f.H = d->h; f.W = d->w; f.C = d->c;
   f.P = d->pad; f.reflect = d->reflect; f.up = d->up; f.dilate = d->dilate;
   f.dact = d->dact; f.accumulate = d->accumulate;
+  {
+    const int lg = ew_lg2(f.C / 4);
+    if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
+      const int rows = f.N * f.H;
+      fold_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(f, lg, rows);
+      GDN_LAUNCH_CHECK("fold_rows_kernel");
+      return GDN_OK;
+    }
+  }
   const long long work = (long long)f.N * f.H * f.W * (f.C / 4);
   fold_grad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(f);
   GDN_LAUNCH_CHECK("fold_grad_kernel");
@@ -655,6 +1213,22 @@ GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float
   if (!d || !w || !out || d->a_pad < d->a || d->b_pad < d->b) return fail(GDN_INVALID_DESC, "gdn_pack_weights: bad arguments");
   PackK k;
   fill_pack(d, k);
+  if (pack_tileable(k)) {
+    const int T = k.kh * k.kw;
+    const size_t smem = (size_t)kPackTile * kPackTile * (T + 1) * sizeof(float);
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+      GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      GDN_CUDA_CHECK(cudaFuncSetAttribute(unpack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured[dev] = true;
+    }
+    dim3 grid((k.Bpad + kPackTile - 1) / kPackTile, (k.Apad + kPackTile - 1) / kPackTile);
+    pack_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
+    GDN_LAUNCH_CHECK("pack_tile_kernel");
+    return GDN_OK;
+  }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.Apad * k.Bpad;
   pack_weights_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
   GDN_LAUNCH_CHECK("pack_weights_kernel");
@@ -665,6 +1239,22 @@ GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* gra
   if (!d || !dw || !grad) return fail(GDN_INVALID_DESC, "gdn_unpack_wgrad: null pointer");
   PackK k;
   fill_pack(d, k);
+  if (pack_tileable(k)) {
+    const int T = k.kh * k.kw;
+    const size_t smem = (size_t)kPackTile * kPackTile * (T + 1) * sizeof(float);
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+      GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      GDN_CUDA_CHECK(cudaFuncSetAttribute(unpack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      configured[dev] = true;
+    }
+    dim3 grid((k.B + kPackTile - 1) / kPackTile, (k.A + kPackTile - 1) / kPackTile);
+    unpack_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dw, grad, k, accumulate);
+    GDN_LAUNCH_CHECK("unpack_tile_kernel");
+    return GDN_OK;
+  }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.A * k.B;
   unpack_wgrad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(dw, grad, k, accumulate);
   GDN_LAUNCH_CHECK("unpack_wgrad_kernel");

@@ -15,6 +15,7 @@ F.interpolate / torch.cat in /root/reference/src/AE_model_unet.py (see graph.py)
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -83,6 +84,7 @@ class Engine:
                 break
         self.units = units
         self.thin_in = graph.cin < 64          # thin inputs go through im2col; wide ones (stand-alone blocks) are tensors
+        self._conv_descs = []
         self._infer_shapes()
         self._plan_tensors()
         self._alloc()
@@ -90,6 +92,8 @@ class Engine:
         if backward:
             self._build_backward()
         self._wversion = None
+        if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+            self.autotune()
 
     # ------------------------------------------------------------------ shapes
     def _infer_shapes(self):
@@ -178,6 +182,8 @@ class Engine:
     # ------------------------------------------------------------------ helpers to emit calls
     def _call(self, fn, desc, what):
         L = self.L
+        if fn is L.gdn_conv2d:
+            self._conv_descs.append((what, desc))
 
         def run(s, fn=fn, desc=desc, what=what):
             rc = fn(C.byref(desc), s)
@@ -512,18 +518,6 @@ class Engine:
             self.bwd.append(self._call(L.gdn_act_backward, b, "act_backward " + u.conv))
             self.grad_ready_op[u.bn + ".weight"] = self.grad_ready_op[u.bn + ".bias"] = len(self.bwd) - 1
             self.launches_bwd += 2
-            need_dgrad = [s for s in u.srcs if not (s == "in" and self.thin_in)]
-            fwd_stride2 = (not u.transposed) and u.stride == 2
-            if fwd_stride2 and need_dgrad:
-                cu.dy_dil = torch.empty((N, 2 * ho, 2 * wo, u.cout), dtype=torch.bfloat16, device=dev)
-                b2 = BnBwdDesc()
-                C.memmove(C.byref(b2), C.byref(b), C.sizeof(b))
-                b2.dy = cu.dy_dil.data_ptr()
-                b2.dilate = 1
-                b2.dgamma = None
-                b2.dbeta = None
-                self.bwd.append(self._call(L.gdn_act_backward, b2, "act_backward(dilated) " + u.conv))
-                self.launches_bwd += 1
             # ---- weight gradient (same geometry as the forward conv)
             wd = WgradDesc()
             fd = cu.conv_desc
@@ -574,6 +568,9 @@ class Engine:
         up, pad_phys, refl, dil = v
         c_s, h_s, w_s = self.shape[s_name]
         # dgrad weight pack: [tap][a = ci of this source][b = co]
+        if (not u.transposed) and u.stride == 2:
+            self._build_dgrad_stride2(u, cu, s_name, c_off, cs, acc)
+            return
         wdg = torch.empty((kk, cs, u.cout), dtype=torch.bfloat16, device=dev)
         if u.transposed:
             # w is (cin, cout, k, k): dX = conv(dy, w) -- no flip
@@ -599,10 +596,7 @@ class Engine:
             direct = True
         else:
             offb = cu.off + pad_phys            # forward offset in buffer coordinates
-            if (not u.transposed) and u.stride == 2:
-                d.src0 = Act(cu.dy_dil.data_ptr(), N, 2 * cu.ho, 2 * cu.wo, u.cout, 0)
-            else:
-                d.src0 = Act(cu.dy.data_ptr(), N, cu.ho, cu.wo, u.cout, 0)
+            d.src0 = Act(cu.dy.data_ptr(), N, cu.ho, cu.wo, u.cout, 0)
             d.stride = 1
             d.off_y = d.off_x = -(k - 1) - offb
             sc = 2 if (up or dil) else 1
@@ -629,6 +623,70 @@ class Engine:
             self.launches_bwd += 2
             cu.keep = getattr(cu, "keep", []) + [tmp]
         cu.keep = getattr(cu, "keep", []) + [wdg]
+
+    def _build_dgrad_stride2(self, u, cu, s_name, c_off, cs, acc):
+        """input gradient of a stride-2 convolution as FOUR stride-1 convolutions over dy (sub-pixel decomposition):
+        the forward reads in[2*o + t + offb], so buffer positions Y with (Y - offb) = 2*i + a only ever meet the taps
+        t = a + 2*m.  Per parity class (ay, ax):  dX[2*i + a + offb] = sum_m dy[i - m] * w[a + 2*m], a ceil((k-a)/2)-tap
+        correlation with the flipped sub-kernel, written with destination stride 2.  No zero-dilated copy of dy and
+        a quarter of the MMAs of the dilated formulation."""
+        L, N, dev, P = self.L, self.N, self.dev, self.P
+        k, kk = cu.k, cu.k * cu.k
+        wt = P[u.conv + ".weight"]
+        up, pad_phys, refl, dil = self._variant(u)
+        assert not up and not dil
+        c_s, h_s, w_s = self.shape[s_name]
+        offb = cu.off + pad_phys
+        Hd, Wd = h_s + 2 * pad_phys, w_s + 2 * pad_phys
+        direct = not refl
+        if direct:
+            tgt = self.dact[s_name]
+        else:
+            tgt = torch.empty((N, Hd, Wd, cs), dtype=torch.float32, device=dev)
+        keep = []
+        for ay in (0, 1):
+            for ax in (0, 1):
+                ky, kx = (k - ay + 1) // 2, (k - ax + 1) // 2
+                if ky <= 0 or kx <= 0:
+                    continue
+                wdg = torch.empty((ky * kx, cs, u.cout), dtype=torch.bfloat16, device=dev)
+                # packed[(r,s)][ci][co] = w[co][c_off + ci][ay + 2*(ky-1-r)][ax + 2*(kx-1-s)]
+                pd = PackDesc(ky, kx, cs, u.cout, cs, u.cout, kk, u.cin * kk, 2 * k, 2, 1, 0)
+                self.pack_ops_bwd.append(self._pack_call(pd, wt, None, wdg, "pack-dgrad-s2 " + u.conv,
+                                                         c_off * kk + ay * k + ax))
+                iy = -((ay + offb) // 2)           # ceil((-a - offb) / 2): first i with a destination >= 0
+                ix = -((ax + offb) // 2)
+                oy, ox = 2 * iy + ay + offb, 2 * ix + ax + offb
+                d = ConvDesc()
+                d.src0 = Act(cu.dy.data_ptr(), N, cu.ho, cu.wo, u.cout, 0)
+                d.weights = wdg.data_ptr()
+                d.kh, d.kw = ky, kx
+                d.stride = 1
+                d.off_y, d.off_x = iy - (ky - 1), ix - (kx - 1)
+                d.out_h, d.out_w = (Hd - oy + 1) // 2, (Wd - ox + 1) // 2
+                d.cout = d.cout_pad = cs
+                d.algo = 0
+                d.dst_h, d.dst_w = Hd, Wd
+                d.dst_sy = d.dst_sx = 2
+                d.dst_oy, d.dst_ox = oy, ox
+                d.out_f32 = tgt.data_ptr()
+                d.resid = tgt.data_ptr() if (direct and acc) else None
+                if d.out_h > 0 and d.out_w > 0:
+                    self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+                    self.launches_bwd += 1
+                keep.append(wdg)
+        if not direct:
+            f = FoldDesc()
+            f.dpad = tgt.data_ptr()
+            f.ctot, f.c_off = cs, 0
+            f.n, f.h, f.w, f.c = N, h_s, w_s, cs
+            f.pad, f.reflect, f.up, f.dilate = pad_phys, refl, 0, 0
+            f.dact = self.dact[s_name].data_ptr()
+            f.accumulate = int(acc)
+            self.bwd.append(self._call(L.gdn_fold_grad, f, "fold " + u.conv))
+            self.launches_bwd += 1
+            keep.append(tgt)
+        cu.keep = getattr(cu, "keep", []) + keep
 
     def _build_head_backward(self, u, cu, have):
         """64 -> 1 head (k9, zero pad 4, tanh): the caller supplies dL/d(pre-tanh) as fp32 (N, H, W); it is im2col'd
@@ -696,6 +754,44 @@ class Engine:
         self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
         self.launches_bwd += 5
         cu.keep = [wdg]
+
+    # (mode, sub-tiles): GDN_CONV_TAPBOX = 1, GDN_CONV_HALO = 2 with J in bits 8-15
+    _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1)
+
+    def autotune(self, reps=3):
+        """Time every staging variant of every implicit-GEMM launch once, on the device, and keep the fastest.  All
+        variants accumulate in the same order, so the choice changes speed only (tile shape vs. wave quantisation
+        on 148 SMs is what decides it: e.g. 16x52 maps of 512 channels run 1.7x faster tap-by-tap than halo-resident).
+        Runs at engine construction, before any real data is in the buffers; GDN_AUTOTUNE=0 keeps the heuristics."""
+        s = _lib.stream_ptr()
+        fn = self.L.gdn_conv2d
+        self.algo_choice = {}
+        cache = {}
+        for what, d in self._conv_descs:
+            key = (d.src0.n, d.src0.h, d.src0.w, d.src0.c, d.src0.pad, d.src1.c if d.src1.ptr else 0, d.kh, d.kw, d.stride,
+                   d.out_h, d.out_w, d.cout_pad, bool(d.out_f32), bool(d.out_bf16.ptr), bool(d.resid), bool(d.stat_sum),
+                   d.dst_sy)
+            if key in cache:
+                d.algo = cache[key]
+                self.algo_choice[what] = d.algo
+                continue
+            best, best_ms = 0, None
+            for algo in self._ALGOS:
+                d.algo = algo
+                if fn(C.byref(d), s) != 0:       # variant not applicable to this geometry
+                    continue
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn(C.byref(d), s)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1)
+                if best_ms is None or ms < best_ms:
+                    best, best_ms = algo, ms
+            d.algo = best
+            cache[key] = best
+            self.algo_choice[what] = best
 
     def profile(self, ops, reps=3):
         """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid"""
