@@ -514,6 +514,15 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   if (d->cout != d->cout_pad && d->cout_pad != 16) return fail(GDN_INVALID_DESC, "gdn_conv2d: padded cout only for the 16-wide head");
   if (two && (d->src1.n != d->src0.n)) return fail(GDN_INVALID_DESC, "gdn_conv2d: source batch mismatch");
   int BN = d->cout_pad >= 256 ? 256 : d->cout_pad;
+  {
+    // bits 16-23 of algo: output-channel tile requested by the caller's autotuner (in units of 64; 0 = widest)
+    const int bn_req = ((d->algo >> 16) & 0xff) * 64;
+    if (bn_req) {
+      if ((bn_req != 64 && bn_req != 128 && bn_req != 256) || bn_req > d->cout_pad || d->cout_pad % bn_req)
+        return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: output-channel tile %d does not divide %d", bn_req, d->cout_pad);
+      BN = bn_req;
+    }
+  }
   if (BN != 16 && BN != 64 && BN != 128 && BN != 256) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout_pad %d", d->cout_pad);
   if (d->cout_pad % BN) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout_pad %d not a multiple of %d", d->cout_pad, BN);
   if (d->cout % 8 && d->cout != 1) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: cout %d", d->cout);

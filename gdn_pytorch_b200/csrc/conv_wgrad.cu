@@ -2,11 +2,12 @@
 //
 //   dW[tap][ci][co] (fp32, +=)  =  sum over pixels  X[pix (+) tap][ci] * dY[pix][co]
 //
-// GEMM view per CTA: D[M = 128 rows, N = 64 output channels] with the pixel index as K.  The 128 rows are a
+// GEMM view per CTA: D[M = 128 rows, N = WN output channels] with the pixel index as K.  The 128 rows are a
 // "unit": TWO (tap, 64-channel chunk) slices of the forward input stacked along M, so the tensor core always runs
-// at M = 128 even for 64-channel layers.  Each CTA owns up to 8 units (8 x 64 = 512 TMEM columns), one 64-wide
-// block of output channels and a contiguous range of pixel tiles (split-K); it accumulates in TMEM over its whole
-// range and flushes once with fp32 atomics.
+// at M = 128 even for 64-channel layers.  WN = 64 / 128 / 256 (the widest that divides Cout: an N = 64 MMA is
+// shared-memory-bandwidth bound at 48 cycles, N >= 128 runs at the tensor pipe's rate).  Each CTA owns up to
+// 512 / WN units (512 TMEM columns), one WN-wide block of output channels and a contiguous range of pixel tiles
+// (split-K); it accumulates in TMEM over its whole range and flushes once with vectorised fp32 reductions.
 //
 // Operand staging (both operands are MN-major: the channel index is contiguous in NHWC, pixels are K):
 //   HALO   (stride 1): the X halo of a 16 x 8J pixel tile is brought in by ONE TMA box per pixel tile; every unit
@@ -60,6 +61,7 @@ struct WRing {
   }
 };
 
+template <int WN>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ WgK p) {
@@ -78,7 +80,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStagesMax; i++) {
       mbar_init(&x_full[i], 1);
-      mbar_init(&x_empty[i], halo ? 2 : 1);   // HALO: both issuers read every X stage; TAPBOX: a stage belongs to one unit
+      mbar_init(&x_empty[i], 2);   // both issuers observe (wait + commit) every X stage, see the MMA loop
       mbar_init(&y_full[i], 1);
       mbar_init(&y_empty[i], 2);
     }
@@ -187,8 +189,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           mbar_wait(&y_empty[ry.i], ry.ph ^ 1);
           mbar_expect_tx(&y_full[ry.i], p.y_bytes);
           uint8_t* dst = sY + (size_t)ry.i * p.y_bytes;
-          for (int j = 0; j < p.J; j++)
-            tma_load_4d(&tmY, &y_full[ry.i], dst + j * 16384, cob * 64, ox0 + 8 * j * (halo ? 1 : 0), oy0, n0);
+          // [co block of 64][sub-tile j][128 pixels][64 co]: the MMA's N index walks the co blocks LBO = J*16 KB apart
+          for (int cb = 0; cb < WN / 64; cb++)
+            for (int j = 0; j < p.J; j++)
+              tma_load_4d(&tmY, &y_full[ry.i], dst + (cb * p.J + j) * 16384, cob * WN + cb * 64,
+                          ox0 + 8 * j * (halo ? 1 : 0), oy0, n0);
           ry.next(p.nstage);
         }
       }
@@ -196,16 +201,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
   } else if (warp == kWgWarpMMA || warp == kWgWarpMMA2) {
     // ------------------------------------------------------------ MMA issuers (whole warp, elected lane issues)
     // Issuer `who` takes units u0 + who, u0 + who + 2, ...; both wait on the same full barriers and commit to the
-    // same empty barriers (arrival count 2), except TAPBOX X stages, which belong to exactly one unit.
+    // same empty barriers (arrival count 2).  That includes TAPBOX X stages, which carry one unit each: the issuer
+    // that does not own the unit still waits and commits, because a parity wait may lag the barrier by at most one
+    // phase -- an issuer that skipped a stage's phase would mistake the phase before it for the one it wants.
     const int who = (warp == kWgWarpMMA) ? 0 : 1;
     WRing rx, ry;
     uint32_t accph = 0;
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    constexpr uint32_t idesc = make_idesc_bf16(128, WN, 1, 1);  // both operands MN-major
     const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
     const uint32_t x_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
-    const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
-    const uint64_t a_hi_tap = make_smem_desc_sw128(0, 16384u, 1024u);
     const int J = p.J;
+    const uint64_t b_hi = make_smem_desc_sw128(0, (uint32_t)J * 16384u, 1024u);
+    const uint64_t a_hi_tap = make_smem_desc_sw128(0, 16384u, 1024u);
     const uint32_t kstep = halo ? (uint32_t)(2 * p.halo_w * 128) >> 4 : (2048u >> 4);  // 16 pixels of K per MMA
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       int g, cic, cob, pt0, pt1;
@@ -228,7 +235,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
             const uint32_t a0 = xb + (uint32_t)(un.rA * p.halo_w + un.sA) * 128u;
             const uint32_t lbo = un.sB < 0 ? 128u : (uint32_t)((un.rB - un.rA) * p.halo_w + (un.sB - un.sA)) * 128u;
             const uint64_t ad0 = make_smem_desc_sw128(a0, lbo, x_sbo);
-            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
+            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * WN);
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < 2; j++) {
@@ -247,20 +254,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           rx.next(p.nstage);
         } else {
           for (int u = u0; u < u1; u++) {
-            if (((u - u0) & 1) == who) {
-              mbar_wait(&x_full[rx.i], rx.ph);
-              tc_fence_after();
-              const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
-              const uint64_t ad0 = a_hi_tap + (uint64_t)((xb & 0x3FFFFu) >> 4);
-              const uint32_t acc = tmem_base + (uint32_t)((u - u0) * 64);
-              if (elect_one()) {
+            mbar_wait(&x_full[rx.i], rx.ph);
+            tc_fence_after();
+            const uint32_t xb = sX_u + (uint32_t)rx.i * p.x_bytes;
+            const uint64_t ad0 = a_hi_tap + (uint64_t)((xb & 0x3FFFFu) >> 4);
+            const uint32_t acc = tmem_base + (uint32_t)((u - u0) * WN);
+            const bool mine = ((u - u0) & 1) == who;
+            if (elect_one()) {
+              if (mine) {
 #pragma unroll
                 for (int ks = 0; ks < 8; ks++)
                   umma_bf16(acc, ad0 + (uint64_t)(ks * 128), bd0 + (uint64_t)(ks * 128), idesc, first_t | (uint32_t)ks);
-                umma_commit(&x_empty[rx.i]);
               }
-              __syncwarp();
+              umma_commit(&x_empty[rx.i]);
             }
+            __syncwarp();
             rx.next(p.nstage);
           }
         }
@@ -293,15 +301,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           const int chunk = halo ? cic : (second ? un.cB : un.cA);
           const int ci = chunk * 64 + (m & 63);
           const int tap = r * p.kw + s;
-          float* dst = p.dw + ((size_t)tap * p.cin_total + ci) * p.cout_pad + cob * 64;
-#pragma unroll
-          for (int cc = 0; cc < 64; cc += 32) {
+          float* dst = p.dw + ((size_t)tap * p.cin_total + ci) * p.cout_pad + cob * WN;
+#pragma unroll 1
+          for (int cc = 0; cc < WN; cc += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((u - u0) * 64 + cc), v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((u - u0) * WN + cc), v);
             tmem_ld_wait();
             if (live) {
 #pragma unroll
-              for (int i = 0; i < 32; i++) atomicAdd(dst + cc + i, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + i), "r"(v[i]), "r"(v[i + 1]),
+                             "r"(v[i + 2]), "r"(v[i + 3])
+                             : "memory");
             }
           }
         }
@@ -344,6 +355,7 @@ using namespace gdn;
 extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn_wgrad_desc* d, gdn_stream stream) {
   if (!d || !d->x0.ptr || !d->dy.ptr || !d->dw) return fail(GDN_INVALID_DESC, "gdn_conv2d_wgrad: null pointer");
   const bool two = d->x1.ptr != nullptr;
+  const int WN = (d->cout_pad % 256 == 0) ? 256 : (d->cout_pad % 128 == 0) ? 128 : 64;
   if (d->x0.c % 64 || (two && d->x1.c % 64) || d->cout_pad % 64 || d->dy.c != d->cout_pad)
     return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d_wgrad: channels must be multiples of 64 (cin %d/%d, cout %d, dy.c %d)",
                 d->x0.c, two ? d->x1.c : 0, d->cout_pad, d->dy.c);
@@ -370,7 +382,8 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
   k.cout_pad = d->cout_pad;
   k.kw = d->kw;
   k.dw = d->dw;
-  k.co_blocks = d->cout_pad / 64;
+  k.co_blocks = d->cout_pad / WN;
+  const int upc_max = 512 / WN;           // units per CTA (tensor memory columns)
 
   const bool halo = (d->stride == 1 && taps > 1 && !two);
   k.mode = halo ? GDN_CONV_HALO : GDN_CONV_TAPBOX;
@@ -399,13 +412,18 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
       const int cols2 = (d->out_w + 15) / 16 * 16;
       if ((cols2 - d->out_w) * 4 >= cols2) J = 1;
     }
-    const int halo_h = 16 + d->kh - 1, halo_w = 8 * J + d->kw - 1;
+    int halo_w = 0;
+    const int halo_h = 16 + d->kh - 1;
+    for (;; J = 1) {
+      halo_w = 8 * J + d->kw - 1;
+      k.x_tx = (uint32_t)halo_h * halo_w * 128;
+      k.x_bytes = k.x_tx + 1024;  // slack for the dummy second half of an unpaired tap
+      k.x_bytes = (k.x_bytes + 1023) & ~1023u;
+      k.y_bytes = (uint32_t)J * 16384 * (WN / 64);
+      if (J == 1 || 2 * ((size_t)k.x_bytes + k.y_bytes) <= smem_budget) break;   // keep at least two stages
+    }
     k.J = J;
     k.halo_w = halo_w;
-    k.x_tx = (uint32_t)halo_h * halo_w * 128;
-    k.x_bytes = k.x_tx + 1024;  // slack for the dummy second half of an unpaired tap
-    k.x_bytes = (k.x_bytes + 1023) & ~1023u;
-    k.y_bytes = (uint32_t)J * 16384;
     k.tiles_x = (d->out_w + 8 * J - 1) / (8 * J);
     k.tiles_y = (d->out_h + 15) / 16;
     k.nb = 1;
@@ -443,7 +461,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
     k.nb = nb;
     k.x_bytes = 32768;
     k.x_tx = 32768;
-    k.y_bytes = 16384;
+    k.y_bytes = 16384 * (WN / 64);
     k.tiles_x = (d->out_w + tw - 1) / tw;
     k.tiles_y = (d->out_h + th - 1) / th;
     k.groups_img = (k.n_img + nb - 1) / nb;
@@ -457,7 +475,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
     if ((rc = wg_act_map(&tmY, d->dy, 1, box))) return rc;
   }
   k.n_units = nu;
-  k.n_groups = (nu + 7) / 8;
+  k.n_groups = (nu + upc_max - 1) / upc_max;
   k.units_per_cta = (nu + k.n_groups - 1) / k.n_groups;
   k.total_pt = k.tiles_x * k.tiles_y * k.groups_img;
   const int items = k.n_groups * k.ci_chunks * k.co_blocks;
@@ -478,12 +496,16 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     configured[dev] = true;
   }
   const size_t smem = (size_t)k.nstage * (k.x_bytes + k.y_bytes) + 1024;
   const int grid = k.total_work < sms ? k.total_work : sms;
-  conv_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
+  if (WN == 256) conv_wgrad_kernel<256><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
+  else if (WN == 128) conv_wgrad_kernel<128><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
+  else conv_wgrad_kernel<64><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
   GDN_LAUNCH_CHECK("conv_wgrad_kernel");
   return GDN_OK;
 }

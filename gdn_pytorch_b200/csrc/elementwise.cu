@@ -324,7 +324,9 @@ __device__ __forceinline__ void act_finish8(const ActFwd& a, float* v, const flo
 }
 
 // source-driven: every source pixel is read once and written to out_f32 and to the interior + reflection images of
-// out_bf16 (no upsampling / dilation).
+// out_bf16 (no upsampling / dilation).  U independent items are in flight per thread (4 without a residual stream,
+// 2 with one) so that ~64 KB of loads are outstanding per SM.
+template <bool RESID, int U>
 __global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
   const int cgm = (1 << lg_cg) - 1;
   const int items = a.W << lg_cg;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, co
     sh[j] = a.scale ? a.shift[c8 + j] : 0.f;
   }
   const int P = a.P, Hp = a.H + 2 * P, Wp = a.W + 2 * P;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int n = row / a.H, y = row - n * a.H;
     int ys[3], ny = 0;
@@ -345,42 +348,46 @@ __global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, co
       if (y >= a.H - 1 - P && y <= a.H - 2) ys[ny++] = P + 2 * (a.H - 1) - y;
     }
     const size_t row_off = (size_t)row * a.W * a.C;
-    for (int it0 = threadIdx.x; it0 < items; it0 += 2 * kEwThreads) {
-      float v[2][8];
-      float4 r0[2], r1[2];
-      bool live[2];
+    for (int it0 = threadIdx.x; it0 < items; it0 += U * kEwThreads) {
+      uint4 q[U];        // 16-bit sources: the raw 16 B; fp32 sources: first float4
+      float4 q1[U];      // fp32 sources: second float4
+      float4 r0[RESID ? U : 1], r1[RESID ? U : 1];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
+      for (int u = 0; u < U; u++) {
         const int it = it0 + u * kEwThreads;
-        live[u] = it < items;
-        if (!live[u]) continue;
+        if (it >= items) continue;
         const size_t off = row_off + (size_t)(it >> lg_cg) * a.C + c8;
         if (a.src_bf16) {
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + off));
-          if (a.src_half) unpack8h(q, v[u]); else unpack8(q, v[u]);
+          q[u] = __ldg(reinterpret_cast<const uint4*>(a.src_bf16 + off));
         } else {
-          const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + off));
-          const float4 p1 = __ldg(reinterpret_cast<const float4*>(a.src_f32 + off + 4));
-          v[u][0] = p0.x; v[u][1] = p0.y; v[u][2] = p0.z; v[u][3] = p0.w;
-          v[u][4] = p1.x; v[u][5] = p1.y; v[u][6] = p1.z; v[u][7] = p1.w;
+          q[u] = __ldg(reinterpret_cast<const uint4*>(a.src_f32 + off));
+          q1[u] = __ldg(reinterpret_cast<const float4*>(a.src_f32 + off + 4));
         }
-        if (a.resid) {
+        if (RESID) {
           r0[u] = __ldg(reinterpret_cast<const float4*>(a.resid + off));
           r1[u] = __ldg(reinterpret_cast<const float4*>(a.resid + off + 4));
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (!live[u]) continue;
-        const int x = (it0 + u * kEwThreads) >> lg_cg;
-        act_finish8(a, v[u], sc, sh, r0[u], r1[u]);
+      for (int u = 0; u < U; u++) {
+        const int it = it0 + u * kEwThreads;
+        if (it >= items) continue;
+        const int x = it >> lg_cg;
+        float v[8];
+        if (a.src_bf16) {
+          if (a.src_half) unpack8h(q[u], v); else unpack8(q[u], v);
+        } else {
+          v[0] = __uint_as_float(q[u].x); v[1] = __uint_as_float(q[u].y); v[2] = __uint_as_float(q[u].z); v[3] = __uint_as_float(q[u].w);
+          v[4] = q1[u].x; v[5] = q1[u].y; v[6] = q1[u].z; v[7] = q1[u].w;
+        }
+        act_finish8(a, v, sc, sh, RESID ? r0[u] : z4, RESID ? r1[u] : z4);
         if (a.out_f32) {
           float* o = a.out_f32 + row_off + (size_t)x * a.C + c8;
-          *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[u][4], v[u][5], v[u][6], v[u][7]);
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         if (a.out_bf16) {
-          const uint4 w = pack8(v[u]);
+          const uint4 w = pack8(v);
           int xs[3], nx = 0;
           xs[nx++] = x + P;
           if (a.reflect) {
@@ -388,8 +395,8 @@ __global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, co
             if (x >= a.W - 1 - P && x <= a.W - 2) xs[nx++] = P + 2 * (a.W - 1) - x;
           }
           for (int p = 0; p < ny; p++)
-            for (int q = 0; q < nx; q++)
-              *reinterpret_cast<uint4*>(a.out_bf16 + (((size_t)n * Hp + ys[p]) * Wp + xs[q]) * a.C + c8) = w;
+            for (int qq = 0; qq < nx; qq++)
+              *reinterpret_cast<uint4*>(a.out_bf16 + (((size_t)n * Hp + ys[p]) * Wp + xs[qq]) * a.C + c8) = w;
         }
       }
     }
@@ -1092,7 +1099,8 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
     if (a.up) lo.out_bf16 = nullptr;
     if (lo.out_f32 || lo.out_bf16) {
       const int rows = a.N * a.H;
-      act_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
+      if (lo.resid) act_rows_kernel<true, 2><<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
+      else act_rows_kernel<false, 4><<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
       GDN_LAUNCH_CHECK("act_rows_kernel");
     }
     if (a.up && a.out_bf16) {

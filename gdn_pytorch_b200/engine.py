@@ -23,6 +23,7 @@ from . import _lib
 from ._lib import Act, ConvDesc, WgradDesc
 from .graph import Graph, Unit
 
+_SYNC_DEBUG = os.environ.get("GDN_SYNC_DEBUG", "0") == "1"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -189,6 +190,11 @@ class Engine:
             rc = fn(C.byref(desc), s)
             if rc:
                 _lib.check(rc, what)
+            if _SYNC_DEBUG:      # GDN_SYNC_DEBUG=1: attribute asynchronous kernel failures to the op that caused them
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise RuntimeError("gdn_b200: kernel failure in '%s' (algo 0x%x): %s" % (what, getattr(desc, "algo", 0), e))
         run.label = what
         return run
 
@@ -460,6 +466,7 @@ class Engine:
             c, h, w = self.shape[t]
             self.dact[t] = torch.empty((N, h, w, c), dtype=torch.float32, device=dev)
         self._dset = {}   # tensor -> bool (runtime: has a gradient been written in this backward pass?)
+        self._pending_add = {}   # tensor -> fp32 buffer still to be added to its gradient by the next dgrad conv
         maxdw = 0
         for u in self.units:
             cu = self.cu[u.conv]
@@ -489,7 +496,12 @@ class Engine:
                 self._build_head_backward(u, cu, have)
                 continue
             # ---- residual identity: d(resid) (+)= g_out
-            if u.resid:
+            if u.resid and u.resid not in have and self._next_grad_is_direct_conv(u):
+                # nothing has been written to d(resid) yet and the next contribution is a plain dgrad conv:
+                # let that conv's epilogue add g_out (its `resid` operand) instead of copying g_out now
+                self._pending_add[u.resid] = g_out
+                have.add(u.resid)
+            elif u.resid:
                 acc = accumulate_flag(u.resid)
                 a = ActFwdDesc()
                 a.src_f32 = g_out.data_ptr()
@@ -559,6 +571,16 @@ class Engine:
                 self._build_dgrad(u, cu, s_name, c_off, cs, accumulate_flag(s_name))
                 c_off += cs
 
+    def _next_grad_is_direct_conv(self, u):
+        """True when the consumer of u.resid that runs next in backward order (the one closest before u in forward
+        order) is a single-source, stride-1, zero-padded convolution -- its dgrad writes d(resid) directly."""
+        idx = self.units.index(u)
+        for v in reversed(self.units[:idx]):
+            if u.resid in v.srcs:
+                return (len(v.srcs) == 1 and v.stride == 1 and not v.transposed and not v.up and not v.reflect
+                        and v.cin >= 64 and not v.tanh)
+        return False
+
     def _build_dgrad(self, u, cu, s_name, c_off, cs, acc):
         """gradient of unit u w.r.t. source tensor s_name (channels [c_off, c_off+cs) of its input)"""
         L, N, dev, P = self.L, self.N, self.dev, self.P
@@ -605,7 +627,11 @@ class Engine:
         if direct:
             tgt = self.dact[s_name]
             d.out_f32 = tgt.data_ptr()
-            d.resid = tgt.data_ptr() if acc else None
+            pend = self._pending_add.pop(s_name, None)
+            if pend is not None:
+                d.resid = pend.data_ptr()
+            else:
+                d.resid = tgt.data_ptr() if acc else None
             self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
             self.launches_bwd += 1
         else:
@@ -757,6 +783,7 @@ class Engine:
 
     # (mode, sub-tiles): GDN_CONV_TAPBOX = 1, GDN_CONV_HALO = 2 with J in bits 8-15
     _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1)
+    _ALGOS_NARROW = (2 | (2 << 8) | (2 << 16), 2 | (1 << 8) | (2 << 16), 1 | (2 << 16))   # 128-wide channel tiles
 
     def autotune(self, reps=3):
         """Time every staging variant of every implicit-GEMM launch once, on the device, and keep the fastest.  All
@@ -776,10 +803,17 @@ class Engine:
                 self.algo_choice[what] = d.algo
                 continue
             best, best_ms = 0, None
-            for algo in self._ALGOS:
+            # wide layers on small maps leave SMs idle with 256-channel tiles: let 128-wide tiles compete
+            small = d.cout_pad >= 256 and d.src0.n * d.out_h * d.out_w * (d.cout_pad // 256) < 128 * 148 * 2
+            for algo in self._ALGOS + (self._ALGOS_NARROW if small else ()):
                 d.algo = algo
                 if fn(C.byref(d), s) != 0:       # variant not applicable to this geometry
                     continue
+                if _SYNC_DEBUG:
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception as e:
+                        raise RuntimeError("gdn_b200: kernel failure autotuning '%s' with algo 0x%x: %s" % (what, algo, e))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(reps):

@@ -62,8 +62,9 @@ typedef struct {
   int32_t out_h, out_w;      /* outputs computed per image */
   int32_t cout;              /* real output channels */
   int32_t cout_pad;          /* channels in the weight tensor (multiple of 16; == cout unless cout < 16) */
-  int32_t algo;              /* GDN_CONV_* in the low byte; bits 8-15: HALO sub-tiles per tile (1, 2, 4) or 0 = library
-                                heuristic.  Every choice produces bit-identical outputs; callers may time them. */
+  int32_t algo;              /* GDN_CONV_* in the low byte; bits 8-15: HALO sub-tiles per tile (1, 2, 4), bits 16-23: output-channel
+                                tile / 64 (1, 2, 4); 0 = library heuristic.  Every choice produces bit-identical
+                                outputs (BN statistics aside: atomics); callers may time them. */
   /* epilogue */
   const float* bias;         /* [cout] or NULL */
   int32_t relu, tanh_out;

@@ -157,6 +157,11 @@ WGRAD_CASES = [
     dict(N=2, H=16, W=40, cin=256, cout=512, k=3, stride=2),
     dict(N=2, H=32, W=64, cin=64, cout=128, k=4, stride=2, reflect=True, pad=1),
     dict(N=2, H=16, W=40, cin=128, cout=128, k=1, cin2=128), dict(N=2, H=16, W=40, cin=256, cout=64, k=1),
+    # many pixel tiles per CTA: the operand rings wrap several times (regression: an MMA issuer that skipped a
+    # stage's barrier phase mistook the phase before it for the one it wanted)
+    dict(N=8, H=64, W=208, cin=128, cout=128, k=1, cin2=128), dict(N=20, H=32, W=104, cin=256, cout=256, k=1, cin2=256),
+    dict(N=20, H=32, W=104, cin=256, cout=512, k=3, stride=2, reflect=True),
+    dict(N=20, H=64, W=208, cin=128, cout=128, k=7), dict(N=20, H=8, W=26, cin=512, cout=512, k=3),
 ]
 
 

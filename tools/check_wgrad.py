@@ -108,6 +108,12 @@ def main():
     ok &= run("wg tap 64->128 k4 s2 reflect", 2, 32, 64, 64, 128, 4, stride=2, pad_mode="reflect")
     ok &= run("wg tap 1x1 concat 128+128->128", 2, 16, 40, 128, 128, 1, cin2=128)
     ok &= run("wg tap 1x1 256->64", 2, 16, 40, 256, 64, 1)
+    if "--big" in sys.argv:
+        for nimg in (2, 8, 20):
+            ok &= run("wg tap 1x1 concat 128+128->128 64x208 B%d" % nimg, nimg, 64, 208, 128, 128, 1, cin2=128)
+        ok &= run("wg tap 1x1 concat 256+256->256 32x104 B20", 20, 32, 104, 256, 256, 1, cin2=256)
+        ok &= run("wg tap 1x1 concat 512+512->512 16x52 B20", 20, 16, 52, 512, 512, 1, cin2=512)
+        ok &= run("wg tap 256->512 k3 s2 32x104 B20", 20, 32, 104, 256, 512, 3, stride=2, pad_mode="reflect")
     if "--time" in sys.argv:
         run("T wg 64->64 k9 128x416 B20", 20, 128, 416, 64, 64, 9, timing=True)
         run("T wg 128->128 k7 64x208 B20", 20, 64, 208, 128, 128, 7, timing=True)
