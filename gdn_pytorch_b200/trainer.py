@@ -87,7 +87,9 @@ class _StepBase:
     CUDA graph: after ``graph_warmup`` eager steps the whole step (weight re-pack, forward, guidance passes, loss,
     backward, Adam) is captured ONCE and then replayed -- ~600 kernel launches become one cudaGraphLaunch, which
     removes the host from the critical path.  Step-dependent Adam scalars and the learning rate live in a 2-float
-    device buffer refreshed before each replay.  Set GDN_GRAPH=0 to run eagerly."""
+    device buffer refreshed before each replay.  With world > 1 the bucketed NCCL all-reduces (issued on the side
+    stream, forked from and joined back into the capturing stream by events) are part of the same graph.
+    Set GDN_GRAPH=0 to run eagerly."""
     graph_warmup = 2
 
     def __init__(self, model, lr, betas, eps, weight_decay, group, bucket_mb):
@@ -114,7 +116,7 @@ class _StepBase:
         self.step_count = 0
         self.launches_per_step = 0
         env = os.environ.get("GDN_GRAPH")
-        self.use_graph = (env != "0") if env is not None else (self.world == 1)
+        self.use_graph = (env != "0")                # also with world > 1: NCCL collectives are captured into the graph
         self._graph = None
         self._static_in = None
         self._static_out = None
@@ -160,6 +162,15 @@ class _StepBase:
         cur = torch.cuda.current_stream(self.dev)
         bi = 0
         nb = len(self.buckets)
+        if getattr(self, "debug_keep_local_grad", False):
+            # test hook (tools/check_ddp.py): finish backward first and keep this shard's own gradient
+            for op in eng.bwd:
+                op(s)
+            self.local_grad = eng.flat_grad.clone()
+            for bi in range(nb):
+                self._launch_bucket(bi, cur)
+            cur.wait_stream(self.comm_stream)
+            return
         for i, op in enumerate(eng.bwd):
             op(s)
             while bi < nb and self.buckets[bi][2] <= i:
@@ -196,8 +207,12 @@ class _StepBase:
             self._static_in = [None if t is None else t.clone() for t in inputs]
             self._graph_shapes = shapes
             torch.cuda.synchronize(self.dev)
+            if self.world > 1:
+                dist.barrier(group=self.group)       # every rank's eager collectives have retired before capture
+                torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 self._static_out = self._eager(*self._static_in)
             self._graph = g
         for st, t in zip(self._static_in, inputs):

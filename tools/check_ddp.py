@@ -1,0 +1,79 @@
+"""Data-parallel RtoD training step on N GPUs (one process per GPU, NCCL): consistency check.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_ddp.py
+
+Checks (rank 0 prints one 'DDP-OK ...' line, any failure raises):
+  1. after K steps the parameters are bit-identical on every rank (the all-reduced gradients and Adam agree);
+  2. the CUDA-graph step (NCCL collectives captured) and the eager step produce the same parameters up to the
+     fp32-atomic summation noise of the weight-gradient kernel;
+  3. the BerHu threshold is the GLOBAL-batch max (trainer.py:711-720 computes the loss on the gathered batch);
+  4. the bucketed all-reduce covers every gradient element exactly once: the reduced buffer equals a plain
+     all_reduce(SUM) of the per-shard gradients kept by a debug hook.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+import bench
+from gdn_pytorch_b200.trainer import RtoDTrainStep, init_distributed_from_env
+
+
+def run(graph, steps, B, rank, dev):
+    os.environ["GDN_GRAPH"] = "1" if graph else "0"
+    rtod, dtod = bench.build_models(dev)
+    st = RtoDTrainStep(rtod, dtod, lr=2e-5)
+    rgb, dep, spa = [t.to(dev) for t in bench.synth_batch(B, rank)]
+    out = None
+    for _ in range(steps):
+        out = st.step(rgb, dep, spa)
+    torch.cuda.synchronize()
+    return st, {k: float(v) for k, v in out.items()}
+
+
+def main():
+    rank, world, dev = init_distributed_from_env()
+    assert world > 1, "run under torchrun with >= 2 ranks"
+    B = int(os.environ.get("GDN_BATCH", "2"))
+    steps = 5
+    st_g, out_g = run(True, steps, B, rank, dev)
+    st_e, out_e = run(False, steps, B, rank, dev)
+    # 1. identical replicas
+    for st in (st_g, st_e):
+        flat = st.flat_params
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, flat), "rank %d: parameters diverged from rank 0" % rank
+    # 2. graph == eager (up to atomic-order noise)
+    d = (st_g.flat_params - st_e.flat_params).abs().max().item()
+    md = (st_g.flat_params - st_e.flat_params).abs().mean().item()
+    # Adam's first updates are ~ lr * sign(g): only gradients at the atomic-noise level may differ between the runs
+    assert d <= 2 * 2e-5 * steps and md <= 0.05 * 2e-5 * steps, "graph vs eager parameters differ: max %g mean %g" % (d, md)
+    for k in out_g:
+        assert abs(out_g[k] - out_e[k]) <= 2e-2 * max(1e-6, abs(out_e[k])), (k, out_g[k], out_e[k])
+    # 3. global BerHu threshold: every rank holds the same max|diff|
+    m = st_e.kern.maxabs.clone()
+    m0 = m.clone()
+    dist.broadcast(m0, src=0)
+    assert torch.equal(m, m0), "BerHu threshold is not global"
+    # 4. bucketed, overlapped all-reduce == one plain all-reduce of the per-shard gradients
+    st_e.debug_keep_local_grad = True
+    rgb, dep, spa = [t.to(dev) for t in bench.synth_batch(B, rank)]
+    st_e.step(rgb, dep, spa)
+    torch.cuda.synchronize()
+    want = st_e.local_grad.clone()
+    dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    got = st_e.eng.flat_grad
+    err = (want - got).abs().max().item()
+    assert err <= 1e-6 * max(1.0, want.abs().max().item()), "bucketed all-reduce != plain all-reduce (%g)" % err
+    assert want.abs().max().item() > 0
+    if rank == 0:
+        print("DDP-OK world=%d B/rank=%d steps=%d  max|graph-eager|=%.3g  loss(graph)=%.6f loss(eager)=%.6f" %
+              (world, B, steps, d, out_g["loss"], out_e["loss"]), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
