@@ -32,6 +32,12 @@ import torch.distributed as dist  # noqa: E402
 H, W = 128, 416
 GFLOP_RTOD_TRAIN = 1595.2   # per image, canonical: 3 x 414.75 + 2 x 175.48
 GFLOP_RTOD_INFER = 414.75 + 175.48
+GFLOP_DTOD_TRAIN = 3 * 339.17
+FULL_H, FULL_W = 384, 1248   # KITTI 375x1242 padded to multiples of 16 (no reference network accepts 375x1242)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the bench shape (B = 20), from
+# the committed `ncu --set full` capture profiles/r01*_ncu_conv64k9.summary.txt; algorithmic bytes are 272.6 MB in
+# (bf16 NHWC) + 272.6 MB out (fp16 raw) -- see DESIGN.md section 6
+DOMINANT_CONV_TRAFFIC_BYTES = None
 
 
 def peaks():
@@ -76,22 +82,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def synth_batch(B, seed):
+def synth_batch(B, seed, h=H, w=W):
     from oracle import synth   # input generators only (shared with the tests); nothing of the oracle is timed here
-    rgb = synth.synth_rgb(B, H, W, seed)
-    dep = synth.synth_depth(B, H, W, seed)
+    rgb = synth.synth_rgb(B, h, w, seed)
+    dep = synth.synth_depth(B, h, w, seed)
     spa = synth.synth_sparse(dep, seed)
     return rgb, dep, spa
 
 
-def build_models(dev):
+def build_models(dev, h=H, w=W):
     import contextlib, io
     from gdn_pytorch_b200 import AE_model_unet as M
     with contextlib.redirect_stdout(io.StringIO()):
         torch.manual_seed(0)
-        rtod = M.AutoEncoder_2(norm="Batch", input_dim=3, height=H, width=W)
+        rtod = M.AutoEncoder_2(norm="Batch", input_dim=3, height=h, width=w)
         torch.manual_seed(1)
-        dtod = M.AutoEncoder_DtoD(norm="Batch", input_dim=1, height=H, width=W)
+        dtod = M.AutoEncoder_DtoD(norm="Batch", input_dim=1, height=h, width=w)
     return rtod.to(dev), dtod.to(dev).eval()
 
 
@@ -190,7 +196,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--workload", default="train", choices=["train", "train_dtod", "infer", "infer_fullres"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -204,10 +210,11 @@ def main():
     rank, world, dev = init_distributed_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
-    B = args.batch or (20 if args.workload == "train" else 8)
-    rgb_h, dep_h, spa_h = [t.pin_memory() for t in synth_batch(B, rank)]
+    B = args.batch or (20 if args.workload.startswith("train") else 8)
+    h, w = (FULL_H, FULL_W) if args.workload == "infer_fullres" else (H, W)
+    rgb_h, dep_h, spa_h = [t.pin_memory() for t in synth_batch(B, rank, h, w)]
     rgb, dep, spa = rgb_h.to(dev), dep_h.to(dev), spa_h.to(dev)
-    rtod, dtod = build_models(dev)
+    rtod, dtod = build_models(dev, h, w)
     launches = [0]
 
     if args.workload == "train":
@@ -227,15 +234,39 @@ def main():
         metric = "RtoD train imgs/s @128x416"
         workload = ("RtoD training step, batch %d per GPU, 128x416 (BASELINE configs[3]): AutoEncoder_2 fwd + 2 frozen "
                     "DtoD encoder passes + loss + bwd + fused Adam" % B)
+    elif args.workload == "train_dtod":
+        from gdn_pytorch_b200.trainer import DtoDTrainStep
+        dtod.train()
+        stepper = DtoDTrainStep(dtod, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+
+        def step_dev():
+            return stepper.step(dep, spa)
+
+        def step_e2e():
+            d = dep_h.to(dev, non_blocking=True)
+            s = spa_h.to(dev, non_blocking=True)
+            return float(stepper.step(d, s)["loss"])
+        h2d = (dep_h.numel() + spa_h.numel()) * 4
+        d2h = 8
+        gflop_img = GFLOP_DTOD_TRAIN
+        metric = "DtoD train imgs/s @128x416"
+        workload = ("DtoD training step, batch %d per GPU, 128x416 (BASELINE configs[2]): AutoEncoder_DtoD fwd + BerHu/"
+                    "Sobel loss + bwd + fused Adam" % B)
     else:
         from gdn_pytorch_b200.module_runtime import encoder_features
         rtod.eval()
+        full = args.workload == "infer_fullres"
 
         def infer(r, d, s):
             with torch.no_grad():
                 out = rtod(r, istrain=False)
-                encoder_features(dtod, out)
-                return ops.eigen_metrics_device(s, d, out, crop=True)[0]
+                if not full:
+                    encoder_features(dtod, out)
+                out8 = ops.eigen_metrics_device(s, d, out, crop=True)[0]
+                if world > 1:                       # "fused error-metric reduction": one 64-byte all-reduce
+                    dist.all_reduce(out8, op=dist.ReduceOp.SUM)
+                    out8 = out8 / world
+                return out8
 
         def step_dev():
             return infer(rgb, dep, spa)
@@ -247,9 +278,15 @@ def main():
             return infer(r, d, s).tolist()
         h2d = (rgb_h.numel() + dep_h.numel() + spa_h.numel()) * 4
         d2h = 64
-        gflop_img = GFLOP_RTOD_INFER
-        metric = "RtoD infer imgs/s @128x416"
-        workload = "RtoD inference batch %d + DtoD guidance features + Eigen metrics, 128x416 (BASELINE configs[1])" % B
+        if full:
+            gflop_img = 414.75 * 9.0
+            metric = "RtoD infer imgs/s @384x1248"
+            workload = ("RtoD inference at KITTI full resolution (375x1242 -> 384x1248), batch %d per GPU + Eigen metrics "
+                        "with all-reduced sums (BASELINE configs[4])" % B)
+        else:
+            gflop_img = GFLOP_RTOD_INFER
+            metric = "RtoD infer imgs/s @128x416"
+            workload = "RtoD inference batch %d + DtoD guidance features + Eigen metrics, 128x416 (BASELINE configs[1])" % B
 
     def barrier():
         if world > 1:
@@ -290,26 +327,31 @@ def main():
         cms, cfl = time_dominant_conv(dev, B)
         achieved = cfl / (cms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<64> (64->64 k9 s1, halo-resident)", "achieved": achieved,
-                "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "traffic": None,
+                "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                "traffic": DOMINANT_CONV_TRAFFIC_BYTES if B == 20 else None,
                 "peak_source": src + " burst bf16 (kernel timed alone)", "ms_per_launch": cms,
-                "step_tflops": gflop_img * B / ms_step / 1e3 * 1e3 / 1e3,
                 "step_frac_of_sustained": (gflop_img * B / (ms_step / 1e3) / 1e3) / sustained}
         roof["step_tflops"] = gflop_img * B / (ms_step / 1e3) / 1e3
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.workload == "train":
+        if world == 1 and not args.no_cpu_baseline and args.workload == "train":   # rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cstep = cpu_step_fn(2)
             cstep()
-            t0 = time.perf_counter()
-            cstep()
-            dt = time.perf_counter() - t0
+            nrep, t0 = 0, time.perf_counter()
+            while nrep < 3 or (time.perf_counter() - t0 < 10.0 and nrep < 8):
+                cstep()
+                nrep += 1
+            dt = (time.perf_counter() - t0) / nrep
             cpu = {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": "1 warm-up + 1 timed RtoD training step at batch 2 (fp32 torch CPU ops, oracle port)"}
+                   "sample": "1 warm-up + %d timed RtoD training steps at batch 2 (fp32 torch CPU ops with all host "
+                             "threads, oracle port of trainer.py:696-768)" % nrep}
         eng = getattr(locals().get("stepper", None), "eng", None)
         if args.workload == "train":
             per_step = (eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) +
                         sum(e.launches_fwd for e in stepper.deng if e is not None) + 2 + 4 + 1)
+        elif args.workload == "train_dtod":
+            per_step = eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) + 2 + 1
         else:
             per_step = sum(e.launches_fwd for e in rtod.__dict__["_gdn_engines"].values()) + \
                 sum(e.launches_fwd for e in dtod.__dict__["_gdn_engines"].values()) + 1
@@ -328,8 +370,13 @@ def main():
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        # CUDA graphs holding captured NCCL kernels are still alive: communicator teardown can dead-lock behind them
+        # (seen on the 2-GPU box), so synchronise, flush and leave without destroy_process_group()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -327,7 +327,7 @@ __device__ __forceinline__ void act_finish8(const ActFwd& a, float* v, const flo
 // out_bf16 (no upsampling / dilation).  U independent items are in flight per thread (4 without a residual stream,
 // 2 with one) so that ~64 KB of loads are outstanding per SM.
 template <bool RESID, int U>
-__global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+__global__ void __launch_bounds__(kEwThreads, 3) act_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
   const int cgm = (1 << lg_cg) - 1;
   const int items = a.W << lg_cg;
   const int c8 = (threadIdx.x & cgm) * 8;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kEwThreads) act_rows_kernel(const ActFwd a, co
 
 // output-driven x2 bilinear upsampling (align_corners=False) with an optional reflection border: one padded output
 // row per CTA iteration; the row's two source rows and the vertical weight are computed once per row.
-__global__ void __launch_bounds__(kEwThreads) act_up_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+__global__ void __launch_bounds__(kEwThreads, 3) act_up_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
   const int cgm = (1 << lg_cg) - 1;
   const int OH = 2 * a.H, OW = 2 * a.W;
   const int P = a.P, Hp = OH + 2 * P, Wp = OW + 2 * P;

@@ -86,6 +86,12 @@ class Engine:
         self.units = units
         self.thin_in = graph.cin < 64          # thin inputs go through im2col; wide ones (stand-alone blocks) are tensors
         self._conv_descs = []
+        # backward runs on two streams: the weight-gradient chain (wgrad + unpack) is independent of the
+        # dgrad -> BatchNorm-backward -> dgrad chain, so its tensor-core kernels overlap the HBM-bound elementwise
+        # kernels of the main chain (they co-reside on an SM: the elementwise CTAs need no shared memory)
+        self.side_stream = None
+        if backward and os.environ.get("GDN_SIDE", "1") != "0":
+            self.side_stream = torch.cuda.Stream(device=self.dev)
         self._infer_shapes()
         self._plan_tensors()
         self._alloc()
@@ -93,6 +99,7 @@ class Engine:
         if backward:
             self._build_backward()
         self._wversion = None
+        self.timeline, self.tl_tag = None, "fwd"
         if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not torch.cuda.is_current_stream_capturing():
             self.autotune()
 
@@ -403,8 +410,20 @@ class Engine:
         for op in self.pack_ops:
             op(s)
         if self.do_bwd:
-            for op in self.pack_ops_bwd:
-                op(s)
+            side = self.side_stream
+            if side is not None and getattr(self, "async_bwd_pack", False):
+                # the dgrad weight packs are only needed by backward: re-pack them on the side stream, under the
+                # forward convolutions (fused training steps set async_bwd_pack; they always run backward next)
+                main = torch.cuda.current_stream(self.dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for op in self.pack_ops_bwd:
+                        op(C.c_void_p(side.cuda_stream))
+                    self._pack_ev = torch.cuda.Event()
+                    self._pack_ev.record(side)
+            else:
+                for op in self.pack_ops_bwd:
+                    op(s)
 
     def _param_version(self):
         return tuple(t._version for t in self.P.values())
@@ -421,8 +440,17 @@ class Engine:
         if ver != self._wversion:
             self.refresh_weights(s)
             self._wversion = ver
-        for op in self.fwd:
-            op(s)
+        tl = getattr(self, "timeline", None)
+        if tl is None:
+            for op in self.fwd:
+                op(s)
+        else:                               # development aid (tools/timeline.py): completion event after every op
+            cur = torch.cuda.current_stream(self.dev)
+            for op in self.fwd:
+                op(s)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(cur)
+                tl.append((getattr(op, "label", "misc"), self.tl_tag, ev))
         if self.train:
             self._wversion = None if self.do_bwd else self._param_version()  # running stats were updated in place
 
@@ -544,8 +572,9 @@ class Engine:
             wd.kh, wd.kw, wd.stride = fd.kh, fd.kw, fd.stride
             wd.off_y, wd.off_x = fd.off_y, fd.off_x
             wd.out_h, wd.out_w, wd.cout_pad = ho, wo, u.cout
-            self.bwd.append(lambda s, dw=dw: dw.zero_())
-            self.bwd.append(self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv))
+            zero_dw = lambda s, dw=dw: dw.zero_()
+            zero_dw.label = "misc"
+            side_ops = [zero_dw, self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv)]
             if cu.thin:
                 up_ = PackDesc(k, k, u.cout, cu.kpad, u.cout, cu.kpad, u.cin * kk, kk, k, 1, 0, u.cin)
             elif u.transposed:
@@ -558,11 +587,12 @@ class Engine:
                 rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr()), 1, s)
                 if rc:
                     _lib.check(rc, "unpack " + name)
-            self.bwd.append(unpack)
-            self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
+            unpack.label = "unpack " + u.conv
+            side_ops.append(unpack)
             self.launches_bwd += 2
             # ---- input gradient(s)
             c_off = 0
+            self._dgrad_conv_end = len(self.bwd)
             for si, s_name in enumerate(u.srcs):
                 cs = self.shape[s_name][0]
                 if s_name == "in" and self.thin_in:
@@ -570,6 +600,13 @@ class Engine:
                     continue
                 self._build_dgrad(u, cu, s_name, c_off, cs, accumulate_flag(s_name))
                 c_off += cs
+            # the weight-gradient group goes right after this unit's dgrad convolution(s): on the side stream it
+            # starts when they have finished and overlaps the fold / BatchNorm-backward kernels that follow
+            pos = self._dgrad_conv_end
+            for op in side_ops:
+                op.side = 1
+            self.bwd[pos:pos] = side_ops
+            self.grad_ready_op[u.conv + ".weight"] = pos + len(side_ops) - 1
 
     def _next_grad_is_direct_conv(self, u):
         """True when the consumer of u.resid that runs next in backward order (the one closest before u in forward
@@ -633,11 +670,13 @@ class Engine:
             else:
                 d.resid = tgt.data_ptr() if acc else None
             self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+            self._dgrad_conv_end = len(self.bwd)
             self.launches_bwd += 1
         else:
             tmp = torch.empty((N, d.out_h, d.out_w, cs), dtype=torch.float32, device=dev)
             d.out_f32 = tmp.data_ptr()
             self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+            self._dgrad_conv_end = len(self.bwd)
             f = FoldDesc()
             f.dpad = tmp.data_ptr()
             f.ctot, f.c_off = cs, 0
@@ -699,6 +738,7 @@ class Engine:
                 d.resid = tgt.data_ptr() if (direct and acc) else None
                 if d.out_h > 0 and d.out_w > 0:
                     self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
+                    self._dgrad_conv_end = len(self.bwd)
                     self.launches_bwd += 1
                 keep.append(wdg)
         if not direct:
@@ -849,6 +889,45 @@ class Engine:
             self.dpre.copy_(dpre.reshape(self.dpre.shape))
         if dout_nhwc is not None:
             self.dact[self.units[-1].out].copy_(dout_nhwc)
+        self.run_backward()
+
+    def run_backward(self, after_op=None):
+        """enqueue the backward plan: main-chain ops on the current stream, the weight-gradient groups on the side
+        stream (each group waits for the main stream's position at its place in the plan; the main stream waits for
+        the side stream at the end).  after_op(i) is called after op i has been enqueued (gradient bucket launches)."""
         s = _lib.stream_ptr()
-        for op in self.bwd:
-            op(s)
+        side = self.side_stream
+        if side is None:
+            for i, op in enumerate(self.bwd):
+                op(s)
+                if after_op is not None:
+                    after_op(i)
+            return
+        main = torch.cuda.current_stream(self.dev)
+        s_side = C.c_void_p(side.cuda_stream)
+        pack_ev = getattr(self, "_pack_ev", None)
+        if pack_ev is not None:         # dgrad weight packs issued on the side stream during forward
+            main.wait_event(pack_ev)
+            self._pack_ev = None
+        side.wait_stream(main)          # fork now: the side stream is part of the step (and of a graph capture) from here on
+        prev_side = False
+        tl = getattr(self, "timeline", None)
+        for i, op in enumerate(self.bwd):
+            if getattr(op, "side", 0):
+                if not prev_side:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    op(s_side)
+                prev_side = True
+            else:
+                op(s)
+                prev_side = False
+            if tl is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(side if prev_side else main)
+                tl.append((getattr(op, "label", "misc"), "bwd-side" if prev_side else "bwd-main", ev))
+            if after_op is not None:
+                after_op(i)
+        main.wait_stream(side)

@@ -128,6 +128,7 @@ class _StepBase:
         _engines(self.model)
         self.eng = get_engine(self.model, self.graph, x, train=True, backward=True, want=())
         eng = self.eng
+        eng.async_bwd_pack = True
         named = list(self.model.named_parameters())
         # the engine's flat gradient uses the same slot layout as flatten_parameters()
         assert eng.flat_grad.numel() == self.flat_params.numel(), (eng.flat_grad.numel(), self.flat_params.numel())
@@ -156,37 +157,42 @@ class _StepBase:
         s = _lib.stream_ptr()
         eng.flat_grad.zero_()
         if self.world == 1:
-            for op in eng.bwd:
-                op(s)
+            eng.run_backward()
             return
         cur = torch.cuda.current_stream(self.dev)
         bi = 0
         nb = len(self.buckets)
         if getattr(self, "debug_keep_local_grad", False):
             # test hook (tools/check_ddp.py): finish backward first and keep this shard's own gradient
-            for op in eng.bwd:
-                op(s)
+            eng.run_backward()
             self.local_grad = eng.flat_grad.clone()
             for bi in range(nb):
                 self._launch_bucket(bi, cur)
             cur.wait_stream(self.comm_stream)
             return
-        for i, op in enumerate(eng.bwd):
-            op(s)
-            while bi < nb and self.buckets[bi][2] <= i:
-                self._launch_bucket(bi, cur)
-                bi += 1
-        while bi < nb:
-            self._launch_bucket(bi, cur)
-            bi += 1
+        state = [0]
+
+        def after_op(i):
+            while state[0] < nb and self.buckets[state[0]][2] <= i:
+                self._launch_bucket(state[0], cur)
+                state[0] += 1
+        eng.run_backward(after_op)
+        while state[0] < nb:
+            self._launch_bucket(state[0], cur)
+            state[0] += 1
         cur.wait_stream(self.comm_stream)
 
     def _launch_bucket(self, bi, cur):
         s0, e0, _ = self.buckets[bi]
         ev = torch.cuda.Event()
         ev.record(cur)
+        self.comm_stream.wait_event(ev)
+        side = getattr(self.eng, "side_stream", None)
+        if side is not None:                 # weight gradients are produced on the engine's side stream
+            ev2 = torch.cuda.Event()
+            ev2.record(side)
+            self.comm_stream.wait_event(ev2)
         with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(ev)
             dist.all_reduce(self.eng.flat_grad[s0:e0], op=dist.ReduceOp.SUM, group=self.group)
 
     def _run(self, inputs):
@@ -263,10 +269,15 @@ class RtoDTrainStep(_StepBase):
         super().__init__(model, lr, betas, eps, weight_decay, group, bucket_mb)
         self.dtod = dtod_model
         self.guidance = guidance and dtod_model is not None
+        self.aux_stream = None
         if self.guidance:
             self.dtod.eval()
             self.dgraph = self.dtod.gdn_graph()
             self.deng = [None, None]
+            if os.environ.get("GDN_SIDE", "1") != "0":
+                # the target-feature pass depends only on the ground truth: it runs on its own stream, its
+                # tensor-core kernels fill the SMs while the RtoD forward is in its HBM-bound BatchNorm passes
+                self.aux_stream = torch.cuda.Stream(device=self.dev)
 
     def _dtod_features(self, slot, x):
         """encoder + bottleneck of the frozen DtoD net only: (x1, x2, x4, x6) is all the loss reads (trainer.py:700,703);
@@ -289,6 +300,12 @@ class RtoDTrainStep(_StepBase):
     def _eager(self, rgb, depths, sparse):
         self._ensure(rgb)
         eng = self.eng
+        ft_tar = None
+        main = torch.cuda.current_stream(self.dev)
+        if self.guidance and self.aux_stream is not None:
+            self.aux_stream.wait_stream(main)
+            with torch.cuda.stream(self.aux_stream), torch.no_grad():
+                ft_tar = self._dtod_features(0, depths)
         eng.forward(rgb)
         _after_train_forward(self.model)
         out = eng.depth()
@@ -299,7 +316,10 @@ class RtoDTrainStep(_StepBase):
         self.kern.loss(0, out, depths, sparse, rgb, dpre=eng.dpre)
         if self.guidance:
             with torch.no_grad():
-                ft_tar = self._dtod_features(0, depths)
+                if ft_tar is None:
+                    ft_tar = self._dtod_features(0, depths)
+                else:
+                    main.wait_stream(self.aux_stream)
                 ft = self._dtod_features(1, out)
             self.kern.latent(ft, ft_tar)
             feat_numels = [float(t.numel()) for t in ft]

@@ -324,3 +324,51 @@ def test_encoder_features_skip_the_decoder():
     assert len(feats) == 4
     for a, b in zip(feats, ref):
         assert relerr(a.permute(0, 3, 1, 2).cpu(), b) <= 1e-2
+
+
+def test_dtod_train_step_against_oracle():
+    """BASELINE configs[2]: one fused DtoD step (trainer.py:427-468) -- BerHu + 3*Sobel loss terms (0.5 %), Adam"""
+    from gdn_pytorch_b200.trainer import DtoDTrainStep
+    from oracle import losses as OL, adam as OA, synth
+    m, sd = _module("AutoEncoder_DtoD", seed=3)
+    m.train()
+    dep = synth.synth_depth(B, H, W, 0)
+    spa = synth.synth_sparse(dep, 0)
+    p0 = {k: v.detach().clone() for k, v in m.named_parameters()}
+    step = DtoDTrainStep(m, lr=2e-5)
+    terms = step.step(dep.to(dev), spa.to(dev))
+    out = step.eng.depth().detach().cpu()
+    ref = OL.dtod_loss(out, dep, spa)
+    for k in ("output_loss", "gradient_loss", "loss"):
+        assert abs(float(terms[k]) - float(ref[k])) <= 5e-3 * abs(float(ref[k])) + 1e-8, k
+    for k in ("upconv4.weight", "res64_up1.main.3.weight", "upconv3.main.0.weight", "downconv1.main.2.weight"):
+        g = step.eng.grad[k].detach()
+        assert float(g.abs().max()) > 0, k
+        p = p0[k].clone()
+        OA.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1, 2e-5)
+        assert torch.allclose(dict(m.named_parameters())[k].detach(), p, rtol=1e-5, atol=1e-8), k
+    for _ in range(3):                       # graph capture + replay path
+        t2 = step.step(dep.to(dev), spa.to(dev))
+    assert np.isfinite(float(t2["loss"]))
+
+
+@pytest.mark.parametrize("name", ["AutoEncoder_2", "AutoEncoder"])
+def test_full_resolution_inference_matches_oracle(name):
+    """BASELINE configs[4] shape: KITTI full resolution 375x1242 -> 384x1248, RtoD inference + metrics"""
+    from oracle import model as OM, metrics as OMET, synth
+    from gdn_pytorch_b200.ops import eigen_metrics_device
+    m, sd = _module(name, seed=5, h=384, w=1248)
+    m.eval()
+    x = synth.synth_rgb(1, 384, 1248, 7)
+    gt = synth.synth_depth(1, 384, 1248, 7)
+    spa = synth.synth_sparse(gt, 7)
+    with torch.no_grad():
+        got = m(x.to(dev), istrain=False)
+        ref = OM.FORWARDS[name](sd, x, istrain=False)
+    assert got.shape == (1, 1, 384, 1248)
+    assert relerr(got.cpu(), ref) <= 1e-2
+    out8, counts = eigen_metrics_device(spa.to(dev), gt.to(dev), got, crop=True)
+    want8, wantc = OMET.eigen_metrics(spa, gt, got.cpu(), crop=True)
+    assert counts.cpu().tolist() == wantc.tolist()           # delta-threshold pixel counts: bit-exact
+    for a, b in zip(out8.tolist(), want8):
+        assert abs(a - b) <= 5e-3 * abs(b) + 1e-9

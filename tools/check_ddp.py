@@ -20,23 +20,28 @@ import bench
 from gdn_pytorch_b200.trainer import RtoDTrainStep, init_distributed_from_env
 
 
+LR = 1e-6   # small on purpose: train-mode networks at random init amplify any perturbation ~70x per pass (DESIGN.md
+            # "Tolerances"), and Adam's first updates are ~ lr * sign(g); with a tiny lr both runs stay on the same
+            # trajectory and only gradients at the fp32-atomic noise level can move differently
+
+
 def run(graph, steps, B, rank, dev):
     os.environ["GDN_GRAPH"] = "1" if graph else "0"
     rtod, dtod = bench.build_models(dev)
-    st = RtoDTrainStep(rtod, dtod, lr=2e-5)
+    st = RtoDTrainStep(rtod, dtod, lr=LR)
     rgb, dep, spa = [t.to(dev) for t in bench.synth_batch(B, rank)]
-    out = None
+    losses = []
     for _ in range(steps):
-        out = st.step(rgb, dep, spa)
+        losses.append(st.step(rgb, dep, spa)["loss"].clone())
     torch.cuda.synchronize()
-    return st, {k: float(v) for k, v in out.items()}
+    return st, [float(v) for v in losses]
 
 
 def main():
     rank, world, dev = init_distributed_from_env()
     assert world > 1, "run under torchrun with >= 2 ranks"
     B = int(os.environ.get("GDN_BATCH", "2"))
-    steps = 5
+    steps = 4          # 2 eager warm-up steps, capture + first replay, second replay
     st_g, out_g = run(True, steps, B, rank, dev)
     st_e, out_e = run(False, steps, B, rank, dev)
     # 1. identical replicas
@@ -48,10 +53,9 @@ def main():
     # 2. graph == eager (up to atomic-order noise)
     d = (st_g.flat_params - st_e.flat_params).abs().max().item()
     md = (st_g.flat_params - st_e.flat_params).abs().mean().item()
-    # Adam's first updates are ~ lr * sign(g): only gradients at the atomic-noise level may differ between the runs
-    assert d <= 2 * 2e-5 * steps and md <= 0.05 * 2e-5 * steps, "graph vs eager parameters differ: max %g mean %g" % (d, md)
-    for k in out_g:
-        assert abs(out_g[k] - out_e[k]) <= 2e-2 * max(1e-6, abs(out_e[k])), (k, out_g[k], out_e[k])
+    assert d <= 2 * LR * steps and md <= 0.05 * LR * steps, "graph vs eager parameters differ: max %g mean %g" % (d, md)
+    for a, b in zip(out_g, out_e):
+        assert abs(a - b) <= 1e-3 * abs(b), ("loss trajectory", out_g, out_e)
     # 3. global BerHu threshold: every rank holds the same max|diff|
     m = st_e.kern.maxabs.clone()
     m0 = m.clone()
@@ -69,10 +73,12 @@ def main():
     assert err <= 1e-6 * max(1.0, want.abs().max().item()), "bucketed all-reduce != plain all-reduce (%g)" % err
     assert want.abs().max().item() > 0
     if rank == 0:
-        print("DDP-OK world=%d B/rank=%d steps=%d  max|graph-eager|=%.3g  loss(graph)=%.6f loss(eager)=%.6f" %
-              (world, B, steps, d, out_g["loss"], out_e["loss"]), flush=True)
+        print("DDP-OK world=%d B/rank=%d steps=%d  |graph-eager| max %.3g mean %.3g (lr %.0e)  loss(graph)=%s loss(eager)=%s" %
+              (world, B, steps, d, md, LR, ["%.6f" % v for v in out_g], ["%.6f" % v for v in out_e]), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)      # captured NCCL kernels are still alive in the CUDA graphs: skip communicator teardown
 
 
 if __name__ == "__main__":
