@@ -5,6 +5,7 @@
 // All tensors are NHWC; 8 bf16 (16 B) or 4 fp32 (16 B) per thread access, grid-stride loops.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstring>
 #include "common.cuh"
 
 namespace gdn {
@@ -951,12 +952,11 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
 constexpr int kPackTile = 16;
 constexpr int kPackMaxTaps = 81;
 
-__global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
-                                                       __nv_bfloat16* __restrict__ out, const PackK k) {
+__device__ __forceinline__ void pack_tile_body(const float* __restrict__ w, const float* __restrict__ scale_a,
+                                               __nv_bfloat16* __restrict__ out, const PackK& k, const int a0, const int b0,
+                                               float* s_tile) {
   // tile[a_local][b_local][tap]; parameter address of (a, b, tap) = a*sa + b*sb + tap  (one of sa / sb is T = taps)
-  extern __shared__ float s_tile[];
   const int T = k.kh * k.kw;
-  const int a0 = blockIdx.y * kPackTile, b0 = blockIdx.x * kPackTile;
   const bool b_inner = (k.sb == T);  // [a][b][taps] (Conv2d)  vs  [b][a][taps] (ConvTranspose2d / dgrad views)
   const int run = kPackTile * T;     // contiguous floats per outer index
   for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
@@ -978,6 +978,39 @@ __global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict_
     if (scale_a && a < k.A) v *= scale_a[a];
     out[((long long)t * k.Apad + a) * k.Bpad + b] = __float2bfloat16(v);
   }
+}
+
+__global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
+                                                       __nv_bfloat16* __restrict__ out, const PackK k) {
+  extern __shared__ float s_tile[];
+  pack_tile_body(w, scale_a, out, k, blockIdx.y * kPackTile, blockIdx.x * kPackTile, s_tile);
+}
+
+// All weight packs of a network in ONE launch: a device table of jobs (one per packed tensor), CTA c works on tile
+// (c - cta0) of the job whose [cta0, cta0 + tiles) range contains it.  A training step re-packs ~90 tensors; as
+// separate launches they are latency-bound (~16 us each), as one launch the whole re-pack is a single HBM-bound pass.
+struct PackJob {
+  PackK k;
+  const float* w;
+  const float* scale_a;
+  __nv_bfloat16* out;
+  int cta0, tiles_x;
+};
+
+__global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restrict__ jobs, const int njobs) {
+  extern __shared__ float s_tile[];
+  __shared__ PackJob job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {  // last job with cta0 <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].cta0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job = jobs[lo];
+  }
+  __syncthreads();
+  const int tile = blockIdx.x - job.cta0;
+  pack_tile_body(job.w, job.scale_a, job.out, job.k, (tile / job.tiles_x) * kPackTile, (tile % job.tiles_x) * kPackTile, s_tile);
 }
 
 // grad[a*sa + b*sb + tap] (+)= dw[t][b][a]
@@ -1240,6 +1273,45 @@ GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.Apad * k.Bpad;
   pack_weights_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
   GDN_LAUNCH_CHECK("pack_weights_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_pack_job_size(void) { return (int)sizeof(PackJob); }
+
+// Fill one entry of a host-side job table (job_out: gdn_pack_job_size() bytes).  *n_ctas receives the number of CTAs
+// the job needs; the caller lays the jobs out back to back (cta0 = running sum) and copies the table to the device.
+// Returns GDN_UNSUPPORTED_SHAPE when the tensor is not tileable (im2col'd thin layers): use gdn_pack_weights for it.
+GDN_API int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, int cta0,
+                              void* job_out, int* n_ctas) {
+  if (!d || !w || !out || !job_out || !n_ctas || d->a_pad < d->a || d->b_pad < d->b)
+    return fail(GDN_INVALID_DESC, "gdn_pack_job_fill: bad arguments");
+  PackJob j;
+  fill_pack(d, j.k);
+  if (!pack_tileable(j.k)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_pack_job_fill: tensor is not tileable");
+  j.w = w;
+  j.scale_a = scale_a;
+  j.out = (__nv_bfloat16*)out;
+  j.cta0 = cta0;
+  j.tiles_x = (j.k.Bpad + kPackTile - 1) / kPackTile;
+  *n_ctas = j.tiles_x * ((j.k.Apad + kPackTile - 1) / kPackTile);
+  memcpy(job_out, &j, sizeof(j));
+  return GDN_OK;
+}
+
+// one launch for a whole device-resident job table (total_ctas = sum of the jobs' CTA counts, max_taps = largest kh*kw)
+GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int max_taps, gdn_stream stream) {
+  if (!jobs_dev || njobs <= 0 || total_ctas <= 0 || max_taps <= 0 || max_taps > kPackMaxTaps)
+    return fail(GDN_INVALID_DESC, "gdn_pack_weights_table: bad arguments");
+  const size_t smem = (size_t)kPackTile * kPackTile * (max_taps + 1) * sizeof(float);
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured[dev] = true;
+  }
+  pack_table_kernel<<<total_ctas, 256, smem, (cudaStream_t)stream>>>((const PackJob*)jobs_dev, njobs);
+  GDN_LAUNCH_CHECK("pack_table_kernel");
   return GDN_OK;
 }
 

@@ -91,13 +91,17 @@ class Engine:
         # kernels of the main chain (they co-reside on an SM: the elementwise CTAs need no shared memory)
         self.side_stream = None
         if backward and os.environ.get("GDN_SIDE", "1") != "0":
-            self.side_stream = torch.cuda.Stream(device=self.dev)
+            self.side_stream = torch.cuda.Stream(device=self.dev, priority=-1)
         self._infer_shapes()
         self._plan_tensors()
         self._alloc()
         self._build_forward()
         if backward:
             self._build_backward()
+        if os.environ.get("GDN_PACK_TABLE", "1") != "0":
+            self.pack_ops = self._batch_packs(self.pack_ops)
+            if backward:
+                self.pack_ops_bwd = self._batch_packs(self.pack_ops_bwd)
         self._wversion = None
         self.timeline, self.tl_tag = None, "fwd"
         if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not torch.cuda.is_current_stream_capturing():
@@ -213,7 +217,42 @@ class Engine:
             rc = L.gdn_pack_weights(C.byref(pd), C.c_void_p(wptr), C.c_void_p(_ptr(scale)), C.c_void_p(out.data_ptr()), s)
             if rc:
                 _lib.check(rc, what)
+        run.pack_job = (pd, wptr, _ptr(scale), out.data_ptr(), what)
+        run.label = "pack"
         return run
+
+    def _batch_packs(self, ops):
+        """replace the per-tensor pack launches in `ops` by ONE table-driven launch (gdn_pack_weights_table); ops that
+        are not packs (eval-mode BatchNorm folds) run first, non-tileable packs (im2col'd thin layers) stay as they are"""
+        L = self.L
+        jsz = L.gdn_pack_job_size()
+        others, left, blobs, cta0, max_taps = [], [], [], 0, 1
+        for op in ops:
+            job = getattr(op, "pack_job", None)
+            if job is None:
+                others.append(op)
+                continue
+            pd, wptr, sptr, optr, what = job
+            buf = C.create_string_buffer(jsz)
+            n = C.c_int(0)
+            rc = L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(wptr), C.c_void_p(sptr), C.c_void_p(optr), cta0, buf, C.byref(n))
+            if rc:
+                left.append(op)
+                continue
+            blobs.append(buf.raw)
+            cta0 += n.value
+            max_taps = max(max_taps, pd.kh * pd.kw)
+        if len(blobs) < 2:
+            return ops
+        table = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(self.dev)
+        njobs, total = len(blobs), cta0
+
+        def run(s, table=table):
+            rc = L.gdn_pack_weights_table(C.c_void_p(table.data_ptr()), njobs, total, max_taps, s)
+            if rc:
+                _lib.check(rc, "pack_weights_table")
+        run.label = "pack-table"
+        return others + [run] + left
 
     # ------------------------------------------------------------------ forward plan
     def _geom(self, u: Unit):
@@ -424,6 +463,13 @@ class Engine:
             else:
                 for op in self.pack_ops_bwd:
                     op(s)
+
+    def refresh_if_stale(self):
+        """re-pack the weights now if the parameters changed since the last pack (forward() then finds them fresh)"""
+        ver = self._param_version()
+        if ver != self._wversion:
+            self.refresh_weights(_lib.stream_ptr())
+            self._wversion = ver
 
     def _param_version(self):
         return tuple(t._version for t in self.P.values())

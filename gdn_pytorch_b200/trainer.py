@@ -113,6 +113,13 @@ class _StepBase:
         self.eng = None
         self.opt = None
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        # Stream priorities: the step's critical chain (forward, dgrad / BatchNorm-backward chain, Adam) runs on a
+        # HIGH priority stream, the weight-gradient chain on a middle one (engine.side_stream) and the frozen DtoD
+        # guidance passes on a low one: pending CTAs of the critical chain are always placed first, the rest fills
+        # whatever SMs it leaves idle (its HBM-bound passes, tails of its persistent kernels).
+        self.main_stream = None
+        if os.environ.get("GDN_SIDE", "1") != "0":
+            self.main_stream = torch.cuda.Stream(device=self.dev, priority=-2)
         self.step_count = 0
         self.launches_per_step = 0
         env = os.environ.get("GDN_GRAPH")
@@ -200,14 +207,14 @@ class _StepBase:
         shapes = tuple(None if t is None else tuple(t.shape) for t in inputs)
         if not self.use_graph:
             self.step_count += 1
-            return self._eager(*inputs)
+            return self._eager_on_main(inputs)
         if self._graph is not None and shapes != self._graph_shapes:
             self._graph = None          # new batch shape: fall back to eager warm-up and re-capture
             self._eager_done = 0
         if self._graph is None and getattr(self, "_eager_done", 0) < self.graph_warmup:
             self._eager_done = getattr(self, "_eager_done", 0) + 1
             self.step_count += 1
-            return self._eager(*inputs)
+            return self._eager_on_main(inputs)
         self.step_count += 1
         if self._graph is None:
             self._static_in = [None if t is None else t.clone() for t in inputs]
@@ -218,7 +225,8 @@ class _StepBase:
                 torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures
-            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
+            kw = {"stream": self.main_stream} if self.main_stream is not None else {}
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global", **kw):
                 self._static_out = self._eager(*self._static_in)
             self._graph = g
         for st, t in zip(self._static_in, inputs):
@@ -226,6 +234,18 @@ class _StepBase:
                 st.copy_(t, non_blocking=True)
         self._graph.replay()
         return self._static_out
+
+    def _eager_on_main(self, inputs):
+        """run the step on the high-priority stream, ordered after / before the caller's current stream"""
+        ms = self.main_stream
+        if ms is None:
+            return self._eager(*inputs)
+        cur = torch.cuda.current_stream(self.dev)
+        ms.wait_stream(cur)
+        with torch.cuda.stream(ms):
+            out = self._eager(*inputs)
+        cur.wait_stream(ms)
+        return out
 
     def _optim_step(self):
         self.opt.grad_scale = 1.0 / self.world     # SUM all-reduce -> average, folded into the Adam kernel
@@ -302,6 +322,7 @@ class RtoDTrainStep(_StepBase):
         eng = self.eng
         ft_tar = None
         main = torch.cuda.current_stream(self.dev)
+        eng.refresh_if_stale()      # forward weight packs first: they are at the head of the critical chain
         if self.guidance and self.aux_stream is not None:
             self.aux_stream.wait_stream(main)
             with torch.cuda.stream(self.aux_stream), torch.no_grad():
@@ -314,17 +335,26 @@ class RtoDTrainStep(_StepBase):
         if self.world > 1:
             dist.all_reduce(self.kern.maxabs, op=dist.ReduceOp.MAX, group=self.group)
         self.kern.loss(0, out, depths, sparse, rgb, dpre=eng.dpre)
-        if self.guidance:
+        if self.guidance and ft_tar is None:
             with torch.no_grad():
-                if ft_tar is None:
-                    ft_tar = self._dtod_features(0, depths)
-                else:
-                    main.wait_stream(self.aux_stream)
+                ft_tar = self._dtod_features(0, depths)
                 ft = self._dtod_features(1, out)
             self.kern.latent(ft, ft_tar)
             feat_numels = [float(t.numel()) for t in ft]
+        elif self.guidance:
+            # the prediction-feature pass and the four feature MSEs feed only the REPORTED latent loss (no gradient:
+            # trainer.py:699-703 runs them under no_grad), so they stay on the low-priority stream, under backward
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.aux_stream), torch.no_grad():
+                self.aux_stream.wait_event(ev)
+                ft = self._dtod_features(1, out)
+                self.kern.latent(ft, ft_tar)
+            feat_numels = [float(t.numel()) for t in ft]
         self._backward_and_reduce()
         self._optim_step()
+        if self.aux_stream is not None:
+            main.wait_stream(self.aux_stream)
         return self.kern.assemble(0, float(out.numel()), feat_numels)
 
 

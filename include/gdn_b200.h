@@ -174,6 +174,15 @@ typedef struct {
 } gdn_pack_desc;
 int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, gdn_stream stream);
 int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* grad, int accumulate, gdn_stream stream);
+/* Batched re-pack: every packed tensor of a network in ONE launch.  The caller builds a job table on the host with
+ * gdn_pack_job_fill (entries of gdn_pack_job_size() bytes, cta0 = running sum of the n_ctas returned so far), copies
+ * it to device memory once, and calls gdn_pack_weights_table after every optimizer step.  Non-tileable tensors
+ * (the im2col'd thin first layers) return GDN_UNSUPPORTED_SHAPE from gdn_pack_job_fill and keep using
+ * gdn_pack_weights. */
+int gdn_pack_job_size(void);
+int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, int cta0, void* job_out,
+                      int* n_ctas);
+int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int max_taps, gdn_stream stream);
 
 /* ---- training loss, metrics, optimizer ------------------------------------------------------------------ */
 

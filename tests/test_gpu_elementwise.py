@@ -250,3 +250,49 @@ def test_pack_weights_and_unpack_wgrad(cout, cin, k, transposed):
     else:
         inc = dw.view(k, k, cin, cout).permute(3, 2, 0, 1)
     assert torch.allclose(grad, before + inc, rtol=0, atol=1e-6)
+
+
+def test_pack_weights_table_matches_per_tensor_packs():
+    """the one-launch job table (every packed tensor of a network) == the per-tensor gdn_pack_weights results"""
+    from gdn_pytorch_b200.engine import PackDesc
+    _lib, L = _L()
+    g = torch.Generator().manual_seed(9)
+    specs = [(64, 64, 9, False, False), (128, 64, 7, False, True), (512, 256, 3, False, False), (128, 256, 1, False, True),
+             (256, 512, 4, True, False), (64, 128, 5, True, False), (256, 256, 5, False, True)]
+    jsz = L.gdn_pack_job_size()
+    blobs, cta0, outs, wants, keep = [], 0, [], [], []
+    for cout, cin, k, transposed, scaled in specs:
+        kk = k * k
+        if transposed:
+            w = torch.randn((cin, cout, k, k), generator=g).to(dev)
+            pd = PackDesc(k, k, cout, cin, cout, cin, kk, cout * kk, k, 1, 1, 0)
+        else:
+            w = torch.randn((cout, cin, k, k), generator=g).to(dev)
+            pd = PackDesc(k, k, cout, cin, cout, cin, cin * kk, kk, k, 1, 0, 0)
+        sc = (torch.rand(cout, generator=g) + 0.5).to(dev) if scaled else None
+        sp = C.c_void_p(sc.data_ptr() if sc is not None else None)
+        want = torch.empty((kk, cout, cin), device=dev, dtype=torch.bfloat16)
+        _lib.check(L.gdn_pack_weights(C.byref(pd), C.c_void_p(w.data_ptr()), sp, C.c_void_p(want.data_ptr()),
+                                      _lib.stream_ptr()), "pack")
+        out = torch.full((kk, cout, cin), float("nan"), device=dev, dtype=torch.bfloat16)
+        buf, n = C.create_string_buffer(jsz), C.c_int(0)
+        _lib.check(L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(w.data_ptr()), sp, C.c_void_p(out.data_ptr()), cta0, buf,
+                                       C.byref(n)), "job_fill")
+        assert n.value == ((cin + 15) // 16) * ((cout + 15) // 16)
+        blobs.append(buf.raw)
+        cta0 += n.value
+        outs.append(out)
+        wants.append(want)
+        keep += [w, sc]
+    table = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(dev)
+    _lib.check(L.gdn_pack_weights_table(C.c_void_p(table.data_ptr()), len(blobs), cta0, 81, _lib.stream_ptr()), "table")
+    torch.cuda.synchronize()
+    for o, w_ in zip(outs, wants):
+        assert torch.equal(o, w_)
+    # an im2col'd thin layer is not tileable: the table builder reports it, the caller keeps gdn_pack_weights for it
+    pd = PackDesc(9, 9, 64, 256, 64, 256, 3 * 81, 81, 9, 1, 0, 3)
+    buf, n = C.create_string_buffer(jsz), C.c_int(0)
+    w = torch.randn((64, 3, 9, 9), generator=g).to(dev)
+    out = torch.empty((1, 64, 256), device=dev, dtype=torch.bfloat16)
+    assert L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(w.data_ptr()), C.c_void_p(None), C.c_void_p(out.data_ptr()), 0, buf,
+                               C.byref(n)) != 0

@@ -22,6 +22,9 @@ st.deng[0].timeline, st.deng[0].tl_tag = tl, "dtod-target"
 st.deng[1].timeline, st.deng[1].tl_tag = tl, "dtod-pred"
 e0 = torch.cuda.Event(enable_timing=True)
 e1 = torch.cuda.Event(enable_timing=True)
+# park the GPU (~40 ms spin) so that the host enqueues the WHOLE step before anything runs: the time line then shows
+# the device's own scheduling (what a CUDA-graph replay sees), not the eager launch rate of the Python host
+torch.cuda._sleep(int(float(os.environ.get("GDN_PARK_MS", "40")) * 1.9e6))
 e0.record()
 st.step(rgb, dep, spa)
 e1.record()
