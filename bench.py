@@ -121,6 +121,8 @@ def time_dominant_conv(dev, B):
     d.out16_is_half = 1
     d.stat_sum, d.stat_sqsum = st[0].data_ptr(), st[1].data_ptr()
     L = _lib.lib()
+    from gdn_pytorch_b200.engine import autotune_conv
+    algo = autotune_conv(L, d)           # the same on-device variant selection the engine applies to every layer
     for _ in range(3):
         _lib.check(L.gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
     torch.cuda.synchronize()
@@ -133,7 +135,7 @@ def time_dominant_conv(dev, B):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * H * W * 64 * 64 * 81
-    return ms, flops
+    return ms, flops, algo
 
 
 def cpu_step_fn(B):
@@ -324,12 +326,14 @@ def main():
 
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        cms, cfl = time_dominant_conv(dev, B)
+        cms, cfl, calgo = time_dominant_conv(dev, B)
         achieved = cfl / (cms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<64> (64->64 k9 s1, halo-resident)", "achieved": achieved,
                 "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                 "traffic": DOMINANT_CONV_TRAFFIC_BYTES if B == 20 else None,
                 "peak_source": src + " burst bf16 (kernel timed alone)", "ms_per_launch": cms,
+                "variant": "algo 0x%x (%s, J=%d%s)" % (calgo, "halo" if (calgo & 0xff) == 2 else "tapbox", (calgo >> 8) & 0xff,
+                                                       ", CTA pairs cta_group::2" if calgo & (1 << 24) else ""),
                 "step_frac_of_sustained": (gflop_img * B / (ms_step / 1e3) / 1e3) / sustained}
         roof["step_tflops"] = gflop_img * B / (ms_step / 1e3) / 1e3
         cpu = None

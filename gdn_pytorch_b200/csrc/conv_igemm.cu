@@ -19,6 +19,14 @@
 //          pixels each) share every weight tile.
 //   TAPBOX (anything: stride 2, 1x1 on a virtual concat of two sources, tiny maps): one TMA box per (tap, chunk).
 // (tools/probe_umma.cu is the hardware check of the descriptor semantics this relies on.)
+//
+// CTA pairs (template CG = 2, HALO mode): two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per step on two
+// adjacent pixel tiles (M = 256) against the same weight tile.  Each CTA stages its own activation halo and only
+// HALF of the weight rows, so the shared-memory operand traffic per MMA drops from 4 KB + BN*32 B to
+// 4 KB + BN*16 B per SM -- an M = 128, N = 64 MMA is shared-memory-bandwidth bound (6 KB per 32-cycle slot against
+// 128 B/clk; measured 48 cycles), the pair needs 5 KB.  The leader CTA (cluster rank 0) issues all MMAs; both CTAs'
+// TMA loads count their bytes on the leader's "full" barriers; tcgen05.commit multicasts to both CTAs' "empty" /
+// "accumulator full" barriers; both CTAs' epilogue warps arrive on the leader's "accumulator empty" barrier.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -99,13 +107,16 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[NV], int lane) {
   return v[0];
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvK p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr uint32_t B_BYTES = BN * 128;
+  // (the dynamic shared memory starts at the same offset in both CTAs of a pair, so the aligned layout is symmetric)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr uint32_t B_BYTES = BN * 128 / CG;   // a pair splits the weight rows between its CTAs
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.na * p.a_bytes;
 
@@ -129,15 +140,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&acc_full[i], p.nmma);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], 4 * CG);   // pair: the epilogue warps of both CTAs release the leader's accumulators
     }
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 2 * (BN >= 32 ? BN : 32); i += kThreads) (&s_stat[0][0])[i] = 0.f;
   __syncwarp();
   if (warp == kWarpMMA) {
-    tmem_alloc(&tmem_base_s, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2sm(&tmem_base_s, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(&tmem_base_s, 512);
+      tmem_relinquish();
+    }
   }
   if (warp == kWarpA && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -145,14 +161,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
   if (warp == kWarpB && lane == 0) tma_prefetch_desc(&tmB);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int acc_stride = p.J * BN;
 
+  // work item -> (output-channel block, pixel tile); a pair works on pixel tiles 2m and 2m + 1 of the same block (the
+  // odd one out lies beyond the last image: its loads are zero-filled, its pixels fail the `valid` test)
+  const int cta_first = blockIdx.x / CG, cta_step = gridDim.x / CG;
   auto decode = [&](int t, int& nblk, int& tx, int& ty, int& img) {
     nblk = t % p.cout_blocks;
     t /= p.cout_blocks;
+    if (CG == 2) t = 2 * t + (int)cta_rank;
     tx = t % p.tiles_x;
     t /= p.tiles_x;
     ty = t % p.tiles_y;
@@ -165,7 +185,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ------------------------------------------------------------------ A producer
     if (lane == 0) {
       Ring ra;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = cta_first; t < p.total_tiles; t += cta_step) {
         int nblk, tx, ty, img;
         decode(t, nblk, tx, ty, img);
         const int oy0 = ty * tile_h, ox0 = tx * tile_w, n0 = img * p.nb;
@@ -177,8 +197,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int ctot = s1 ? p.c1_total : p.c0_total;
           if (halo) {
             mbar_wait(&a_empty[ra.i], ra.ph ^ 1);
-            mbar_expect_tx(&a_full[ra.i], p.a_bytes);
-            tma_load_4d(tm, &a_full[ra.i], sA + (size_t)ra.i * p.a_bytes, cc * 64, ox0 + offx, oy0 + offy, img);
+            if (CG == 2) {
+              if (leader) mbar_expect_tx(&a_full[ra.i], 2 * p.a_bytes);
+              tma_load_4d_2sm(tm, &a_full[ra.i], sA + (size_t)ra.i * p.a_bytes, cc * 64, ox0 + offx, oy0 + offy, img);
+            } else {
+              mbar_expect_tx(&a_full[ra.i], p.a_bytes);
+              tma_load_4d(tm, &a_full[ra.i], sA + (size_t)ra.i * p.a_bytes, cc * 64, ox0 + offx, oy0 + offy, img);
+            }
             ra.next(p.na);
           } else {
             for (int r = 0; r < p.kh; r++)
@@ -204,14 +229,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ------------------------------------------------------------------ B producer (weights)
     if (lane == 0) {
       Ring rb;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = cta_first; t < p.total_tiles; t += cta_step) {
         int nblk, tx, ty, img;
         decode(t, nblk, tx, ty, img);
         for (int c = 0; c < chunks; c++)
           for (int tap = 0; tap < taps; tap++) {
             mbar_wait(&b_empty[rb.i], rb.ph ^ 1);
-            mbar_expect_tx(&b_full[rb.i], B_BYTES);
-            tma_load_3d(&tmB, &b_full[rb.i], sB + (size_t)rb.i * B_BYTES, c * 64, nblk * BN, tap);
+            if (CG == 2) {
+              if (leader) mbar_expect_tx(&b_full[rb.i], 2 * B_BYTES);
+              tma_load_3d_2sm(&tmB, &b_full[rb.i], sB + (size_t)rb.i * B_BYTES, c * 64, nblk * BN + (int)cta_rank * (BN / 2), tap);
+            } else {
+              mbar_expect_tx(&b_full[rb.i], B_BYTES);
+              tma_load_3d(&tmB, &b_full[rb.i], sB + (size_t)rb.i * B_BYTES, c * 64, nblk * BN, tap);
+            }
             rb.next(p.nbst);
           }
       }
@@ -224,9 +254,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // Issuer `who` owns sub-tiles [j0, j1) of every tile; every issuer waits on the same full barriers and
     // commits to the same empty barriers (their arrival count is the number of issuers).
     const int who = (warp == kWarpMMA) ? 0 : 1;
-    if (who < p.nmma) {
+    if (who < p.nmma && leader) {
       Ring ra, rb, rc;
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(128 * CG, BN, 0, 0);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (CG == 2) umma_bf16_2sm(d, a, b, id, acc); else umma_bf16(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (CG == 2) umma_commit_2sm(bar, 3); else umma_commit(bar);
+      };
       const uint32_t a_sbo = halo ? (uint32_t)p.halo_w * 128u : 1024u;
       const uint64_t a_hi = make_smem_desc_sw128(0, 0, a_sbo);
       const uint64_t b_hi = make_smem_desc_sw128(0, 0, 1024u);
@@ -238,7 +274,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int kh = p.kh, kw = p.kw, na = p.na, nbst = p.nbst;
       const uint32_t a_bytes = p.a_bytes;
       const uint32_t row_skip = halo ? (uint32_t)(p.halo_w - kw) * 128u : 0u;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = cta_first; t < p.total_tiles; t += cta_step) {
         mbar_wait(&acc_empty[rc.i], rc.ph ^ 1);
         tc_fence_after();
         const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride) + acc_j0;
@@ -262,22 +298,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   for (int j = 0; j < 4; j++)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++)
-                      umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
-                                idesc, k4 ? 1u : accum);
+                      mma(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
+                          idesc, k4 ? 1u : accum);
                 } else if (jn == 2) {
 #pragma unroll
                   for (int j = 0; j < 2; j++)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++)
-                      umma_bf16(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
-                                idesc, k4 ? 1u : accum);
+                      mma(acc_addr + (uint32_t)(j * BN), ad0 + (uint64_t)(j * 64 + k4 * 2), bd0 + (uint64_t)(k4 * 2),
+                          idesc, k4 ? 1u : accum);
                 } else {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; k4++)
-                    umma_bf16(acc_addr, ad0 + (uint64_t)(k4 * 2), bd0 + (uint64_t)(k4 * 2), idesc, k4 ? 1u : accum);
+                    mma(acc_addr, ad0 + (uint64_t)(k4 * 2), bd0 + (uint64_t)(k4 * 2), idesc, k4 ? 1u : accum);
                 }
-                umma_commit(&b_empty[rb.i]);
-                if (!halo) umma_commit(&a_empty[ra.i]);
+                commit(&b_empty[rb.i]);
+                if (!halo) commit(&a_empty[ra.i]);
               }
               __syncwarp();
               accum = 1u;
@@ -288,12 +324,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             a_off += row_skip;
           }
           if (halo) {
-            if (elect_one()) umma_commit(&a_empty[ra.i]);
+            if (elect_one()) commit(&a_empty[ra.i]);
             __syncwarp();
             ra.next(na);
           }
         }
-        if (elect_one()) umma_commit(&acc_full[rc.i]);
+        if (elect_one()) commit(&acc_full[rc.i]);
         __syncwarp();
         rc.next(p.acc_bufs);
       }
@@ -305,7 +341,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int q = warp;
     const int m = q * 32 + lane;
     const bool do_stats = p.stat_sum != nullptr;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = cta_first; t < p.total_tiles; t += cta_step) {
       int nblk, tx, ty, img;
       decode(t, nblk, tx, ty, img);
       mbar_wait(&acc_full[rc.i], rc.ph);
@@ -434,7 +470,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[rc.i]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&acc_empty[rc.i]); else mbar_arrive(&acc_empty[rc.i]);
+      }
       rc.next(p.acc_bufs);
       if (do_stats && p.cout_blocks > 1) {
         // the channel block changes from tile to tile: flush the per-CTA partials now (4 epilogue warps only)
@@ -459,8 +497,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == kWarpMMA) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) {
+    cluster_sync_all();   // neither CTA may leave (or free tensor memory) while its partner still works on the pair
+    if (warp == kWarpMMA) tmem_dealloc_2sm(tmem_base, 512);
+  } else {
+    __syncthreads();
+    if (warp == kWarpMMA) tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -484,18 +527,35 @@ static int make_act_map(CUtensorMap* tm, const gdn_act& a, int stride, const uin
   return encode_tmap_bf16(tm, a.ptr, 5, dims, str, box);
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvK& k, size_t smem,
                   cudaStream_t st) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     configured[dev] = true;
   }
-  int grid = k.total_tiles < device_sm_count() ? k.total_tiles : device_sm_count();
-  conv_igemm_kernel<BN><<<grid, kThreads, smem, st>>>(a0, a1, b, k);
+  const int slots = device_sm_count() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  const int units = k.total_tiles < slots ? k.total_tiles : slots;
+  if (CG == 1) {
+    conv_igemm_kernel<BN, CG><<<units, kThreads, smem, st>>>(a0, a1, b, k);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(units * CG);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    GDN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CG>, a0, a1, b, k));
+  }
   GDN_LAUNCH_CHECK("conv_igemm_kernel");
   return GDN_OK;
 }
@@ -571,15 +631,18 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: reflection border %d >= extent", d->out_bf16.pad);
 
   int mode = d->algo & 0xff;
+  const int cg = ((d->algo >> 24) & 1) ? 2 : 1;   // bit 24 of algo: CTA pairs (tcgen05 cta_group::2), HALO mode only
   const int j_req = (d->algo >> 8) & 0xff;  // HALO: sub-tiles per tile requested by the caller's autotuner (0 = heuristic)
   const int taps = d->kh * d->kw;
   if (mode == GDN_CONV_AUTO)
     mode = (d->stride == 1 && !two && taps > 1 && d->out_h >= 16 && d->out_w >= 16) ? GDN_CONV_HALO : GDN_CONV_TAPBOX;
   if (mode == GDN_CONV_HALO && (d->stride != 1 || two)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: HALO needs stride 1, one source");
   k.mode = mode;
+  if (cg == 2 && (mode != GDN_CONV_HALO || BN < 64))
+    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: CTA pairs need the HALO mode and >= 64 output channels per tile");
 
   const size_t smem_budget = 227 * 1024 - 4096 - 1024;  // dynamic smem minus alignment slack
-  const uint32_t b_bytes = BN * 128;
+  const uint32_t b_bytes = BN * 128 / cg;
   CUtensorMap tmA0, tmA1, tmB;
   int rc;
   if (mode == GDN_CONV_HALO) {
@@ -611,7 +674,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     k.tiles_x = (d->out_w + 8 * J - 1) / (8 * J);
     k.tiles_y = (d->out_h + 15) / 16;
     k.nb = 1;
-    k.total_tiles = k.tiles_x * k.tiles_y * k.n_img * k.cout_blocks;
+    k.total_tiles = (k.tiles_x * k.tiles_y * k.n_img + cg - 1) / cg * k.cout_blocks;   // work items (pairs when cg = 2)
     uint32_t box[4] = {64, (uint32_t)halo_w, (uint32_t)halo_h, 1};
     if ((rc = make_act_map(&tmA0, d->src0, 1, box))) return rc;
     tmA1 = tmA0;
@@ -650,15 +713,22 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     const uint64_t cin_total = (uint64_t)d->src0.c + (two ? d->src1.c : 0);
     uint64_t dims[3] = {cin_total, (uint64_t)d->cout_pad, (uint64_t)taps};
     uint64_t str[2] = {cin_total * 2, cin_total * 2 * d->cout_pad};
-    uint32_t box[3] = {64, (uint32_t)BN, 1};
+    uint32_t box[3] = {64, (uint32_t)(BN / cg), 1};
     if ((rc = encode_tmap_bf16(&tmB, const_cast<void*>(d->weights), 3, dims, str, box))) return rc;
   }
   const size_t smem = (size_t)k.na * k.a_bytes + (size_t)k.nbst * b_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
+  if (cg == 2) {
+    switch (BN) {
+      case 64: return launch<64, 2>(tmA0, tmA1, tmB, k, smem, st);
+      case 128: return launch<128, 2>(tmA0, tmA1, tmB, k, smem, st);
+      default: return launch<256, 2>(tmA0, tmA1, tmB, k, smem, st);
+    }
+  }
   switch (BN) {
-    case 16: return launch<16>(tmA0, tmA1, tmB, k, smem, st);
-    case 64: return launch<64>(tmA0, tmA1, tmB, k, smem, st);
-    case 128: return launch<128>(tmA0, tmA1, tmB, k, smem, st);
-    default: return launch<256>(tmA0, tmA1, tmB, k, smem, st);
+    case 16: return launch<16, 1>(tmA0, tmA1, tmB, k, smem, st);
+    case 64: return launch<64, 1>(tmA0, tmA1, tmB, k, smem, st);
+    case 128: return launch<128, 1>(tmA0, tmA1, tmB, k, smem, st);
+    default: return launch<256, 1>(tmA0, tmA1, tmB, k, smem, st);
   }
 }

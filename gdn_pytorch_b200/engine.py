@@ -867,51 +867,21 @@ class Engine:
         self.launches_bwd += 5
         cu.keep = [wdg]
 
-    # (mode, sub-tiles): GDN_CONV_TAPBOX = 1, GDN_CONV_HALO = 2 with J in bits 8-15
-    _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1)
-    _ALGOS_NARROW = (2 | (2 << 8) | (2 << 16), 2 | (1 << 8) | (2 << 16), 1 | (2 << 16))   # 128-wide channel tiles
-
     def autotune(self, reps=3):
         """Time every staging variant of every implicit-GEMM launch once, on the device, and keep the fastest.  All
         variants accumulate in the same order, so the choice changes speed only (tile shape vs. wave quantisation
         on 148 SMs is what decides it: e.g. 16x52 maps of 512 channels run 1.7x faster tap-by-tap than halo-resident).
         Runs at engine construction, before any real data is in the buffers; GDN_AUTOTUNE=0 keeps the heuristics."""
-        s = _lib.stream_ptr()
-        fn = self.L.gdn_conv2d
         self.algo_choice = {}
         cache = {}
         for what, d in self._conv_descs:
             key = (d.src0.n, d.src0.h, d.src0.w, d.src0.c, d.src0.pad, d.src1.c if d.src1.ptr else 0, d.kh, d.kw, d.stride,
                    d.out_h, d.out_w, d.cout_pad, bool(d.out_f32), bool(d.out_bf16.ptr), bool(d.resid), bool(d.stat_sum),
                    d.dst_sy)
-            if key in cache:
-                d.algo = cache[key]
-                self.algo_choice[what] = d.algo
-                continue
-            best, best_ms = 0, None
-            # wide layers on small maps leave SMs idle with 256-channel tiles: let 128-wide tiles compete
-            small = d.cout_pad >= 256 and d.src0.n * d.out_h * d.out_w * (d.cout_pad // 256) < 128 * 148 * 2
-            for algo in self._ALGOS + (self._ALGOS_NARROW if small else ()):
-                d.algo = algo
-                if fn(C.byref(d), s) != 0:       # variant not applicable to this geometry
-                    continue
-                if _SYNC_DEBUG:
-                    try:
-                        torch.cuda.synchronize()
-                    except Exception as e:
-                        raise RuntimeError("gdn_b200: kernel failure autotuning '%s' with algo 0x%x: %s" % (what, algo, e))
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    fn(C.byref(d), s)
-                e1.record()
-                e1.synchronize()
-                ms = e0.elapsed_time(e1)
-                if best_ms is None or ms < best_ms:
-                    best, best_ms = algo, ms
-            d.algo = best
-            cache[key] = best
-            self.algo_choice[what] = best
+            if key not in cache:
+                cache[key] = autotune_conv(self.L, d, reps, what)
+            d.algo = cache[key]
+            self.algo_choice[what] = d.algo
 
     def profile(self, ops, reps=3):
         """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid"""
@@ -977,3 +947,45 @@ class Engine:
             if after_op is not None:
                 after_op(i)
         main.wait_stream(side)
+
+
+# ------------------------------------------------------------------------------------------- conv autotuning
+# algo word of gdn_conv_desc: bits 0-7 mode (GDN_CONV_TAPBOX = 1, GDN_CONV_HALO = 2), bits 8-15 HALO sub-tiles J,
+# bits 16-23 output-channel tile / 64 (0 = widest), bit 24 CTA pairs (tcgen05 cta_group::2)
+_PAIR = 1 << 24
+_ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1,
+          2 | (4 << 8) | _PAIR, 2 | (2 << 8) | _PAIR, 2 | (1 << 8) | _PAIR)
+_ALGOS_NARROW = (2 | (2 << 8) | (2 << 16), 2 | (1 << 8) | (2 << 16), 1 | (2 << 16),   # 128-wide channel tiles
+                 2 | (2 << 8) | (2 << 16) | _PAIR, 2 | (1 << 8) | (2 << 16) | _PAIR)
+
+
+def autotune_conv(L, d, reps=3, what="conv"):
+    """fastest algo word for one gdn_conv_desc (timed on the device with CUDA events); leaves d.algo set to it"""
+    s = _lib.stream_ptr()
+    fn = L.gdn_conv2d
+    pairs_ok = os.environ.get("GDN_PAIRS", "1") != "0"
+    best, best_ms = 0, None
+    # wide layers on small maps leave SMs idle with 256-channel tiles: let 128-wide tiles compete
+    small = d.cout_pad >= 256 and d.src0.n * d.out_h * d.out_w * (d.cout_pad // 256) < 128 * 148 * 2
+    for algo in _ALGOS + (_ALGOS_NARROW if small else ()):
+        if (algo & _PAIR) and not pairs_ok:
+            continue
+        d.algo = algo
+        if fn(C.byref(d), s) != 0:       # variant not applicable to this geometry
+            continue
+        if _SYNC_DEBUG:
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:
+                raise RuntimeError("gdn_b200: kernel failure autotuning '%s' with algo 0x%x: %s" % (what, algo, e))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn(C.byref(d), s)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best_ms is None or ms < best_ms:
+            best, best_ms = algo, ms
+    d.algo = best
+    return best

@@ -100,6 +100,14 @@ CONV_CASES = [
     dict(N=2, H=32, W=64, cin=128, cout=64, k=7, reflect=True, algo=2, reflect_out=3),
     dict(N=2, H=32, W=64, cin=64, cout=1, k=9, algo=2),
     dict(N=1, H=48, W=72, cin=64, cout=64, k=9, reflect_out=4, relu=True),
+    # CTA pairs (tcgen05 cta_group::2, algo bit 24): even / odd numbers of pixel tiles, every channel-tile width
+    dict(N=2, H=32, W=64, cin=64, cout=64, k=9, algo=2 | (4 << 8) | (1 << 24), stats=True),
+    dict(N=3, H=16, W=40, cin=64, cout=64, k=3, algo=2 | (1 << 8) | (1 << 24), relu=True, bias=True, resid=True),
+    dict(N=1, H=48, W=72, cin=64, cout=64, k=9, algo=2 | (2 << 8) | (1 << 24), reflect_out=4, relu=True),
+    dict(N=3, H=32, W=48, cin=128, cout=128, k=7, algo=2 | (2 << 8) | (1 << 24), stats=True),
+    dict(N=1, H=32, W=40, cin=256, cout=256, k=5, algo=2 | (1 << 8) | (1 << 24), resid=True, stats=True),
+    dict(N=3, H=16, W=52, cin=512, cout=512, k=3, algo=2 | (2 << 8) | (2 << 16) | (1 << 24), stats=True),
+    dict(N=2, H=32, W=64, cin=128, cout=64, k=7, reflect=True, algo=2 | (4 << 8) | (1 << 24), reflect_out=3),
 ]
 
 

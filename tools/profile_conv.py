@@ -8,5 +8,5 @@ import bench
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-ms, fl = bench.time_dominant_conv(dev, B)
-print("conv 64->64 k9 B=%d: %.4f ms  %.1f TFLOP/s" % (B, ms, fl / ms / 1e9))
+ms, fl, algo = bench.time_dominant_conv(dev, B)
+print("conv 64->64 k9 B=%d: %.4f ms  %.1f TFLOP/s  algo 0x%x" % (B, ms, fl / ms / 1e9, algo))
