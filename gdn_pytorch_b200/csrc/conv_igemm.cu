@@ -20,7 +20,7 @@
 //   TAPBOX (anything: stride 2, 1x1 on a virtual concat of two sources, tiny maps): one TMA box per (tap, chunk).
 // (tools/probe_umma.cu is the hardware check of the descriptor semantics this relies on.)
 //
-// CTA pairs (template CG = 2, HALO mode): two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per step on two
+// CTA pairs (template CG = 2): two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per step on two
 // adjacent pixel tiles (M = 256) against the same weight tile.  Each CTA stages its own activation halo and only
 // HALF of the weight rows, so the shared-memory operand traffic per MMA drops from 4 KB + BN*32 B to
 // 4 KB + BN*16 B per SM -- an M = 128, N = 64 MMA is shared-memory-bandwidth bound (6 KB per 32-cycle slot against
@@ -209,15 +209,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             for (int r = 0; r < p.kh; r++)
               for (int s = 0; s < p.kw; s++) {
                 mbar_wait(&a_empty[ra.i], ra.ph ^ 1);
-                mbar_expect_tx(&a_full[ra.i], p.a_bytes);
+                if (CG == 1 || leader) mbar_expect_tx(&a_full[ra.i], CG * p.a_bytes);
                 uint8_t* dst = sA + (size_t)ra.i * p.a_bytes;
                 if (p.stride == 1) {
-                  tma_load_4d(tm, &a_full[ra.i], dst, cc * 64, ox0 + s + offx, oy0 + r + offy, n0);
+                  if (CG == 2) tma_load_4d_2sm(tm, &a_full[ra.i], dst, cc * 64, ox0 + s + offx, oy0 + r + offy, n0);
+                  else tma_load_4d(tm, &a_full[ra.i], dst, cc * 64, ox0 + s + offx, oy0 + r + offy, n0);
                 } else {
                   // 5D view (2C, Wp/2, 2, Hp/2, N): buffer x = 2*ox + s + off -> (x >> 1, x & 1)
                   const int bx = s + offx, by = r + offy;
                   const int fx = bx >> 1, px = bx & 1, fy = by >> 1, py = by & 1;  // arithmetic shift = floor
-                  tma_load_5d(tm, &a_full[ra.i], dst, px * ctot + cc * 64, ox0 + fx, py, oy0 + fy, n0);
+                  if (CG == 2) tma_load_5d_2sm(tm, &a_full[ra.i], dst, px * ctot + cc * 64, ox0 + fx, py, oy0 + fy, n0);
+                  else tma_load_5d(tm, &a_full[ra.i], dst, px * ctot + cc * 64, ox0 + fx, py, oy0 + fy, n0);
                 }
                 ra.next(p.na);
               }
@@ -638,8 +640,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     mode = (d->stride == 1 && !two && taps > 1 && d->out_h >= 16 && d->out_w >= 16) ? GDN_CONV_HALO : GDN_CONV_TAPBOX;
   if (mode == GDN_CONV_HALO && (d->stride != 1 || two)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: HALO needs stride 1, one source");
   k.mode = mode;
-  if (cg == 2 && (mode != GDN_CONV_HALO || BN < 64))
-    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: CTA pairs need the HALO mode and >= 64 output channels per tile");
+  if (cg == 2 && BN < 64) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: CTA pairs need >= 64 output channels per tile");
 
   const size_t smem_budget = 227 * 1024 - 4096 - 1024;  // dynamic smem minus alignment slack
   const uint32_t b_bytes = BN * 128 / cg;
@@ -700,7 +701,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     k.tiles_x = (d->out_w + tw - 1) / tw;
     k.tiles_y = (d->out_h + th - 1) / th;
     const int groups = (k.n_img + nb - 1) / nb;
-    k.total_tiles = k.tiles_x * k.tiles_y * groups * k.cout_blocks;
+    k.total_tiles = (k.tiles_x * k.tiles_y * groups + cg - 1) / cg * k.cout_blocks;   // work items (pairs when cg = 2)
     uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)nb};
     if ((rc = make_act_map(&tmA0, d->src0, d->stride, box))) return rc;
     if (two) {

@@ -5,6 +5,7 @@
 // All tensors are NHWC; 8 bf16 (16 B) or 4 fp32 (16 B) per thread access, grid-stride loops.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -27,8 +28,18 @@ static inline int ew_lg2(int v) {  // log2 of a power of two, -1 otherwise
   return l;
 }
 
+static inline int ew_row_mult() {   // CTAs per SM of the row kernels (GDN_EW_ROW_MULT, experiment knob; default 8)
+  static int m = 0;
+  if (!m) {
+    const char* e = getenv("GDN_EW_ROW_MULT");
+    m = e ? atoi(e) : 8;
+    if (m < 1) m = 8;
+  }
+  return m;
+}
+
 static inline int ew_row_grid(long long rows) {
-  const long long cap = (long long)device_sm_count() * 8;
+  const long long cap = (long long)device_sm_count() * ew_row_mult();
   return (int)(rows < cap ? (rows < 1 ? 1 : rows) : cap);
 }
 

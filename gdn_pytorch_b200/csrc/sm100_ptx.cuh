@@ -118,6 +118,14 @@ __device__ __forceinline__ void tma_load_4d_2sm(const void* tmap, uint64_t* bar,
       "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2sm(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA store)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

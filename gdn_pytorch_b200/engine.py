@@ -954,9 +954,9 @@ class Engine:
 # bits 16-23 output-channel tile / 64 (0 = widest), bit 24 CTA pairs (tcgen05 cta_group::2)
 _PAIR = 1 << 24
 _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1,
-          2 | (4 << 8) | _PAIR, 2 | (2 << 8) | _PAIR, 2 | (1 << 8) | _PAIR)
+          2 | (4 << 8) | _PAIR, 2 | (2 << 8) | _PAIR, 2 | (1 << 8) | _PAIR, 1 | _PAIR)
 _ALGOS_NARROW = (2 | (2 << 8) | (2 << 16), 2 | (1 << 8) | (2 << 16), 1 | (2 << 16),   # 128-wide channel tiles
-                 2 | (2 << 8) | (2 << 16) | _PAIR, 2 | (1 << 8) | (2 << 16) | _PAIR)
+                 2 | (2 << 8) | (2 << 16) | _PAIR, 2 | (1 << 8) | (2 << 16) | _PAIR, 1 | (2 << 16) | _PAIR)
 
 
 def autotune_conv(L, d, reps=3, what="conv"):

@@ -108,6 +108,11 @@ CONV_CASES = [
     dict(N=1, H=32, W=40, cin=256, cout=256, k=5, algo=2 | (1 << 8) | (1 << 24), resid=True, stats=True),
     dict(N=3, H=16, W=52, cin=512, cout=512, k=3, algo=2 | (2 << 8) | (2 << 16) | (1 << 24), stats=True),
     dict(N=2, H=32, W=64, cin=128, cout=64, k=7, reflect=True, algo=2 | (4 << 8) | (1 << 24), reflect_out=3),
+    dict(N=5, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24), relu=True, bias=True, resid=True, stats=True),
+    dict(N=3, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (2 << 16) | (1 << 24), stats=True),
+    dict(N=2, H=32, W=64, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24)),
+    dict(N=3, H=16, W=40, cin=256, cout=512, k=3, stride=2, algo=1 | (1 << 24), stats=True),
+    dict(N=3, H=16, W=40, cin=128, cout=64, k=1, algo=1 | (1 << 24), cin2=128, stats=True),
 ]
 
 
