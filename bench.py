@@ -181,18 +181,43 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "RtoD train imgs/s @128x416", "value": v, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "RtoD training step (AutoEncoder_2 + 2 frozen DtoD passes + loss + bwd + Adam), 128x416, "
-                               "CPU sample batch %d per step" % B},
+        "config": {"workload": RTOD_TRAIN_WORKLOAD % 20, "batch_per_gpu": 20, "parallelism": "dp%d" % args.gpus,
+                   "l2": "n/a (CPU arm)", "cpu_sample_batch": B},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": "batch %d per step, fp32 torch CPU ops via the oracle port of the reference step "
                                    "(/root/reference is not present on the GPU box)" % B},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+RTOD_TRAIN_WORKLOAD = ("RtoD training step, batch %d per GPU, 128x416 (BASELINE configs[3]): AutoEncoder_2 fwd + 2 frozen "
+                       "DtoD encoder passes + loss + bwd + fused Adam")
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the driver wants exactly ONE JSON line there.
+    Everything written to stdout from here on goes to stderr; emit() writes the JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -234,8 +259,7 @@ def main():
         d2h = 8
         gflop_img = GFLOP_RTOD_TRAIN
         metric = "RtoD train imgs/s @128x416"
-        workload = ("RtoD training step, batch %d per GPU, 128x416 (BASELINE configs[3]): AutoEncoder_2 fwd + 2 frozen "
-                    "DtoD encoder passes + loss + bwd + fused Adam" % B)
+        workload = RTOD_TRAIN_WORKLOAD % B
     elif args.workload == "train_dtod":
         from gdn_pytorch_b200.trainer import DtoDTrainStep
         dtod.train()
@@ -372,7 +396,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # CUDA graphs holding captured NCCL kernels are still alive: communicator teardown can dead-lock behind them
         # (seen on the 2-GPU box), so synchronise, flush and leave without destroy_process_group()
