@@ -34,10 +34,11 @@ GFLOP_RTOD_TRAIN = 1595.2   # per image, canonical: 3 x 414.75 + 
 GFLOP_RTOD_INFER = 414.75 + 175.48
 GFLOP_DTOD_TRAIN = 3 * 339.17
 FULL_H, FULL_W = 384, 1248   # KITTI 375x1242 padded to multiples of 16 (no reference network accepts 375x1242)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the bench shape (B = 20), from
-# the committed `ncu --set full` capture profiles/r01*_ncu_conv64k9.summary.txt; algorithmic bytes are 272.6 MB in
-# (bf16 NHWC) + 272.6 MB out (fp16 raw) -- see DESIGN.md section 6
-DOMINANT_CONV_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the bench shape (B = 20) from
+# the committed `ncu --set full` capture (profiles/r01m_ncu_conv.summary.txt: conv_igemm_kernel<64, 2>, 137.1 MB
+# read + 88.2 MB written while the kernel runs -- part of the output is still in L2 when it ends).  Algorithmic
+# bytes: 136.3 MB in (bf16 NHWC) + 136.3 MB out (fp16 raw) + 0.66 MB weights -- DESIGN.md section 6.
+DOMINANT_CONV_TRAFFIC_BYTES = 225.3e6
 
 
 def peaks():
@@ -381,8 +382,8 @@ def main():
         elif args.workload == "train_dtod":
             per_step = eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) + 2 + 1
         else:
-            per_step = sum(e.launches_fwd for e in rtod.__dict__["_gdn_engines"].values()) + \
-                sum(e.launches_fwd for e in dtod.__dict__["_gdn_engines"].values()) + 1
+            per_step = sum(e.launches_fwd for e in rtod.__dict__.get("_gdn_engines", {}).values()) + \
+                sum(e.launches_fwd for e in dtod.__dict__.get("_gdn_engines", {}).values()) + 1
         line = {
             "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -165,6 +165,58 @@ __global__ void __launch_bounds__(kEwThreads) im2col_rows_kernel(const float* __
   }
 }
 
+// shared-memory path (the one the networks use): the kh input rows an output row needs are staged ONCE per output row
+// in shared memory, pixel-interleaved ([row][x + pad][c], borders already reflected / zeroed), so that the kw*C columns
+// of one tap row are a contiguous run: column k of pixel x is s_rows[off(k) + x*C] with off(k) from a small table.
+// A warp writes one pixel's kpad columns with consecutive lanes on consecutive columns: conflict-free shared-memory
+// reads and fully coalesced 2-byte stores -- the kernel is bound by the HBM write of the column matrix.
+__global__ void __launch_bounds__(kEwThreads) im2col_smem_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                 int N, int C, int H, int W, int kh, int kw, int pad,
+                                                                 int reflect, int kpad) {
+  extern __shared__ float s_rows[];   // [kh][(W + 2*pad) * C]
+  const int Wp = W + 2 * pad;
+  const int rowstride = Wp * C;
+  const int kreal = kh * kw * C, kwc = kw * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int off[8];                         // kpad <= 256: at most 8 columns per lane
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = j * 32 + lane;
+    off[j] = (k < kreal && k < kpad) ? (k / kwc) * rowstride + (k % kwc) : -1;
+  }
+  const int nj = kpad >> 5;
+  const int rows = N * H, plane = H * W;
+  const int fill = kh * rowstride;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, y = row - n * H;
+    const float* img = src + (size_t)n * C * plane;
+    __syncthreads();
+    for (int i = threadIdx.x; i < fill; i += kEwThreads) {
+      const int r = i / rowstride, rem = i - r * rowstride;
+      const int c = rem / Wp, xp = rem - c * Wp;      // channel-major over the row: global reads run along x
+      int yy = y + r - pad, xx = xp - pad;
+      bool ok = true;
+      if (reflect) {
+        yy = reflect_idx(yy, H);
+        xx = reflect_idx(xx, W);
+      } else {
+        ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+      }
+      s_rows[r * rowstride + xp * C + c] = ok ? __ldg(img + c * plane + yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16* drow = dst + (size_t)row * W * kpad;
+    for (int x = warp; x < W; x += kEwThreads / 32) {
+      const float* base = s_rows + x * C;
+      __nv_bfloat16* o = drow + (size_t)x * kpad + lane;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (j < nj) o[j * 32] = __float2bfloat16(off[j] >= 0 ? base[off[j]] : 0.f);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- BN finalize
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -1082,6 +1134,22 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
   if (!src || !dst || c < 1 || c > 4 || kpad % 64 || kh * kw * c > kpad)
     return fail(GDN_INVALID_DESC, "gdn_im2col: bad arguments (c=%d kpad=%d)", c, kpad);
   if (reflect && (pad >= h || pad >= w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_im2col: reflection pad %d >= extent", pad);
+  {
+    const size_t smem = (size_t)kh * (w + 2 * pad) * c * sizeof(float);
+    if (kpad <= 256 && smem <= 96 * 1024 && (long long)h * w * c < (1ll << 31)) {
+      static bool configured[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < 64 && !configured[dev]) {
+        GDN_CUDA_CHECK(cudaFuncSetAttribute(im2col_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured[dev] = true;
+      }
+      im2col_smem_kernel<<<ew_row_grid((long long)n * h), kEwThreads, smem, (cudaStream_t)stream>>>(
+          src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad);
+      GDN_LAUNCH_CHECK("im2col_smem_kernel");
+      return GDN_OK;
+    }
+  }
   if (kh < 256 && kw < 256 && (long long)h * w * c < (1ll << 31)) {
     im2col_rows_kernel<<<ew_row_grid((long long)n * h), kEwThreads, kpad * sizeof(int), (cudaStream_t)stream>>>(
         src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad);

@@ -222,37 +222,44 @@ class Engine:
         return run
 
     def _batch_packs(self, ops):
-        """replace the per-tensor pack launches in `ops` by ONE table-driven launch (gdn_pack_weights_table); ops that
-        are not packs (eval-mode BatchNorm folds) run first, non-tileable packs (im2col'd thin layers) stay as they are"""
+        """replace the per-tensor pack launches in `ops` by table-driven launches (gdn_pack_weights_table), one per
+        kernel size (the table kernel's shared-memory tile is sized by the tap count: one table for everything would
+        run the many 3x3 layers at the occupancy of a 9x9 tile).  Ops that are not packs (eval-mode BatchNorm folds)
+        run first; non-tileable packs (im2col'd thin layers) stay as they are."""
         L = self.L
         jsz = L.gdn_pack_job_size()
-        others, left, blobs, cta0, max_taps = [], [], [], 0, 1
+        others, left, groups = [], [], {}
         for op in ops:
             job = getattr(op, "pack_job", None)
             if job is None:
                 others.append(op)
                 continue
             pd, wptr, sptr, optr, what = job
+            grp = groups.setdefault(pd.kh * pd.kw, {"blobs": [], "cta0": 0})
             buf = C.create_string_buffer(jsz)
             n = C.c_int(0)
-            rc = L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(wptr), C.c_void_p(sptr), C.c_void_p(optr), cta0, buf, C.byref(n))
+            rc = L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(wptr), C.c_void_p(sptr), C.c_void_p(optr), grp["cta0"], buf,
+                                     C.byref(n))
             if rc:
                 left.append(op)
                 continue
-            blobs.append(buf.raw)
-            cta0 += n.value
-            max_taps = max(max_taps, pd.kh * pd.kw)
-        if len(blobs) < 2:
+            grp["blobs"].append(buf.raw)
+            grp["cta0"] += n.value
+        if sum(len(g["blobs"]) for g in groups.values()) < 2:
             return ops
-        table = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).to(self.dev)
-        njobs, total = len(blobs), cta0
+        runs = []
+        for taps, grp in sorted(groups.items()):
+            if not grp["blobs"]:
+                continue
+            table = torch.frombuffer(bytearray(b"".join(grp["blobs"])), dtype=torch.uint8).to(self.dev)
 
-        def run(s, table=table):
-            rc = L.gdn_pack_weights_table(C.c_void_p(table.data_ptr()), njobs, total, max_taps, s)
-            if rc:
-                _lib.check(rc, "pack_weights_table")
-        run.label = "pack-table"
-        return others + [run] + left
+            def run(s, table=table, njobs=len(grp["blobs"]), total=grp["cta0"], taps=taps):
+                rc = L.gdn_pack_weights_table(C.c_void_p(table.data_ptr()), njobs, total, taps, s)
+                if rc:
+                    _lib.check(rc, "pack_weights_table")
+            run.label = "pack-table"
+            runs.append(run)
+        return others + runs + left
 
     # ------------------------------------------------------------------ forward plan
     def _geom(self, u: Unit):
@@ -402,6 +409,24 @@ class Engine:
                     a.n, a.h, a.w, a.c = N, ho, wo, u.cout
                     if first and self.need_f32[u.out]:
                         a.out_f32 = self.f32[u.out].data_ptr()
+                    if v is not None and v[0]:
+                        # x2 bilinear variant: BatchNorm / ReLU / residual ONCE at low resolution into a plain bf16
+                        # buffer, then a pure interpolation pass over it (4 cached 16-byte taps per output vector)
+                        # instead of normalising every tap of every output again
+                        plain = (0, 0, 0, 0)
+                        if (u.out, plain) not in self.act:
+                            self.act[(u.out, plain)] = torch.empty((N, ho, wo, u.cout), dtype=torch.bfloat16, device=dev)
+                        a.out_bf16 = self.act[(u.out, plain)].data_ptr()
+                        self.fwd.append(self._call(L.gdn_act_forward, a, "act " + u.conv))
+                        b = ActFwdDesc()
+                        b.src_bf16 = self.act[(u.out, plain)].data_ptr()
+                        b.n, b.h, b.w, b.c = N, ho, wo, u.cout
+                        b.out_bf16 = self.act[(u.out, v)].data_ptr()
+                        b.up, b.pad, b.reflect, b.dilate = v
+                        self.fwd.append(self._call(L.gdn_act_forward, b, "act-up " + u.conv))
+                        self.launches_fwd += 2
+                        first = False
+                        continue
                     if v is not None:
                         a.out_bf16 = self.act[(u.out, v)].data_ptr()
                         a.up, a.pad, a.reflect, a.dilate = v
