@@ -223,27 +223,65 @@ __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __re
   if (threadIdx.x == 0) atomicAdd(out, acc[0]);
 }
 
-// ---------------------------------------------------------------------------------------- Eigen metrics
-// One block per image.  Arithmetic follows calculate_error.py:32-101 operation by operation in fp32.
+// ---------------------------------------------------------------------------------------- depth metrics
+// One block per image.  Arithmetic follows calculate_error.py operation by operation in fp32.
+//   VAR 0  compute_errors        (KITTI / Eigen, :10-103)   out8 = abs_diff abs_rel sq_rel a1 a2 a3 rmse rmse_log
+//   VAR 1  compute_errors_NYU    (:105-151)                 out8 = abs_diff abs_rel log10  a1 a2 a3 rmse rmse_log
+//   VAR 2  compute_errors_Make3D (:153-182)                 out8 = abs_diff abs_rel log10  -  -  -  rmse -
 struct MetricK {
-  const float* gt_np;  // [B][H][W] sparse / raw ground truth in [-1,1]
+  const float* gt_np;  // [B][H][W] sparse / raw ground truth (unused by VAR 1)
   const float* gt;     // [B][H][W] dense ground truth
   const float* pred;   // [B][H][W]
   int B, H, W;
   int crop, cy1, cy2, cx1, cx2;
-  double* out;         // [8] += per-image metric / B : abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log
+  double* out;         // [8] += per-image metric / B
   long long* counts;   // [B][4] = n_valid, n(<1.25), n(<1.25^2), n(<1.25^3)
 };
 
-__device__ __forceinline__ float norm80(float v, float lo, float hi) {
-  return __fmul_rn(__fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo)), 80.f);
+struct MinMax {
+  float gmin, gmax, pmin, pmax, nmin, nmax;
+};
+
+__device__ __forceinline__ float norm_s(float v, float lo, float hi, float s) {
+  return __fmul_rn(__fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo)), s);
+}
+
+// validity of pixel i and the (gt, pred) pair the medians / metrics are computed on, before median scaling
+template <int VAR>
+__device__ __forceinline__ bool metric_pixel(const MetricK& m, const MinMax& mm, const float* __restrict__ gtn,
+                                             const float* __restrict__ g, const float* __restrict__ p, int i, float& vg,
+                                             float& vp) {
+  const int y = i / m.W, x = i - y * m.W;
+  bool valid;
+  if (VAR == 0) {
+    vg = norm_s(g[i], mm.gmin, mm.gmax, 80.f);                                          // :39,44
+    const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);       // :41,46
+    valid = (n80 < 80.f) && (vg < 80.f) && (n80 > 1.f) && (vg > 1.f);                   // :78
+    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
+    if (valid) vp = norm_s(p[i], mm.pmin, mm.pmax, 80.f);
+  } else if (VAR == 1) {
+    vg = norm_s(g[i], mm.gmin, mm.gmax, 10.f);                                          // :122,125
+    valid = (vg < 10.f) && (vg > 0.f);                                                  // :128
+    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
+    if (valid) vp = norm_s(p[i], mm.pmin, mm.pmax, 10.f);
+  } else {
+    const float g1 = __fdiv_rn(__fsub_rn(g[i], mm.gmin), __fsub_rn(mm.gmax, mm.gmin));     // :163
+    const float n1 = __fdiv_rn(__fsub_rn(gtn[i], mm.nmin), __fsub_rn(mm.nmax, mm.nmin));   // :165
+    const float g80 = __fmul_rn(g1, 80.f), n80 = __fmul_rn(n1, 80.f);
+    valid = (n1 > 1e-2f) && (g1 > 1e-2f) && (n80 < 80.f) && (g80 < 80.f);               // :166,171
+    if (valid) {
+      vg = fminf(fmaxf(g80, 1e-2f), 80.f);                                              // :173
+      vp = fminf(fmaxf(norm_s(p[i], mm.pmin, mm.pmax, 80.f), 1e-2f), 80.f);             // :174
+    }
+  }
+  return valid;
 }
 
 // k-th smallest (0-based) of the valid values via 4-pass radix select on the (non-negative) float bit patterns
-template <bool PRED>
-__device__ float select_kth(const MetricK& m, const float* __restrict__ gtn, const float* __restrict__ g,
-                            const float* __restrict__ p, float gmin, float gmax, float pmin, float pmax, long long kth,
-                            unsigned int* hist /* [256] smem */, unsigned int* s_prefix, long long* s_k) {
+template <int VAR, bool PRED>
+__device__ float select_kth(const MetricK& m, const MinMax& mm, const float* __restrict__ gtn, const float* __restrict__ g,
+                            const float* __restrict__ p, long long kth, unsigned int* hist /* [256] smem */,
+                            unsigned int* s_prefix, long long* s_k) {
   const int HW = m.H * m.W;
   unsigned int prefix = 0, mask = 0;
   long long k = kth;
@@ -251,14 +289,9 @@ __device__ float select_kth(const MetricK& m, const float* __restrict__ gtn, con
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      const int y = i / m.W, x = i - y * m.W;
-      const float g80 = norm80(g[i], gmin, gmax);
-      const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
-      bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
-      if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
-      if (!valid) continue;
-      const float v = PRED ? norm80(p[i], pmin, pmax) : g80;
-      const unsigned int bits = __float_as_uint(v);
+      float vg, vp;
+      if (!metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) continue;
+      const unsigned int bits = __float_as_uint(PRED ? vp : vg);
       if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
     }
     __syncthreads();
@@ -281,53 +314,59 @@ __device__ float select_kth(const MetricK& m, const float* __restrict__ gtn, con
   return __uint_as_float(prefix);
 }
 
+template <int VAR>
 __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m) {
   const int b = blockIdx.x;
   const int HW = m.H * m.W;
-  const float* gtn = m.gt_np + (long long)b * HW;
+  const float* gtn = m.gt_np ? m.gt_np + (long long)b * HW : nullptr;
   const float* g = m.gt + (long long)b * HW;
   const float* p = m.pred + (long long)b * HW;
-  __shared__ float s_f[4][32];
+  __shared__ float s_f[6][32];
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix;
   __shared__ long long s_k;
   __shared__ double sred[32 * 9];
-  __shared__ float s_mm[4];
-  // 1. min / max of pred and gt (calculate_error.py:38-39)
-  float gmin = INFINITY, gmax = -INFINITY, pmin = INFINITY, pmax = -INFINITY;
+  __shared__ float s_mm[6];
+  // 1. per-image min / max (calculate_error.py:38-39 and the NYU / Make3D equivalents)
+  float v[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     const float gv = g[i], pv = p[i];
-    gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
-    pmin = fminf(pmin, pv); pmax = fmaxf(pmax, pv);
+    v[0] = fminf(v[0], gv); v[1] = fmaxf(v[1], gv);
+    v[2] = fminf(v[2], pv); v[3] = fmaxf(v[3], pv);
+    if (VAR == 2) {
+      const float nv = gtn[i];
+      v[4] = fminf(v[4], nv); v[5] = fmaxf(v[5], nv);
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
-    pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      const float t = __shfl_xor_sync(0xffffffffu, v[j], o);
+      v[j] = (j & 1) ? fmaxf(v[j], t) : fminf(v[j], t);
+    }
   }
-  if (lane == 0) { s_f[0][warp] = gmin; s_f[1][warp] = gmax; s_f[2][warp] = pmin; s_f[3][warp] = pmax; }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 6; j++) s_f[j][warp] = v[j];
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < nw; w++) {
-      s_f[0][0] = fminf(s_f[0][0], s_f[0][w]); s_f[1][0] = fmaxf(s_f[1][0], s_f[1][w]);
-      s_f[2][0] = fminf(s_f[2][0], s_f[2][w]); s_f[3][0] = fmaxf(s_f[3][0], s_f[3][w]);
+    for (int j = 0; j < 6; j++) {
+      float r = s_f[j][0];
+      for (int w = 1; w < nw; w++) r = (j & 1) ? fmaxf(r, s_f[j][w]) : fminf(r, s_f[j][w]);
+      s_mm[j] = r;
     }
-    s_mm[0] = s_f[0][0]; s_mm[1] = s_f[1][0]; s_mm[2] = s_f[2][0]; s_mm[3] = s_f[3][0];
   }
   __syncthreads();
-  gmin = s_mm[0]; gmax = s_mm[1]; pmin = s_mm[2]; pmax = s_mm[3];
+  MinMax mm;
+  mm.gmin = s_mm[0]; mm.gmax = s_mm[1]; mm.pmin = s_mm[2]; mm.pmax = s_mm[3]; mm.nmin = s_mm[4]; mm.nmax = s_mm[5];
   // 2. number of valid pixels
   double cnt[1] = {0.0};
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int y = i / m.W, x = i - y * m.W;
-    const float g80 = norm80(g[i], gmin, gmax);
-    const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
-    bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
-    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
-    if (valid) cnt[0] += 1.0;
+    float vg, vp;
+    if (metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) cnt[0] += 1.0;
   }
   block_sum_d<1>(cnt, sred);
   __shared__ long long s_n;
@@ -338,28 +377,24 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
     if (threadIdx.x == 0 && m.counts) { for (int j = 0; j < 4; j++) m.counts[b * 4 + j] = 0; }
     return;  // the reference would produce NaNs here; callers treat n_valid == 0 as "no measurement"
   }
-  // 3. lower medians (torch.median), calculate_error.py:86
+  // 3. lower medians (torch.median), calculate_error.py:86 / :134 / :175
   const long long kth = (nvalid - 1) / 2;
-  const float med_g = select_kth<false>(m, gtn, g, p, gmin, gmax, pmin, pmax, kth, hist, &s_prefix, &s_k);
-  const float med_p = select_kth<true>(m, gtn, g, p, gmin, gmax, pmin, pmax, kth, hist, &s_prefix, &s_k);
+  const float med_g = select_kth<VAR, false>(m, mm, gtn, g, p, kth, hist, &s_prefix, &s_k);
+  const float med_p = select_kth<VAR, true>(m, mm, gtn, g, p, kth, hist, &s_prefix, &s_k);
   // 4. metrics
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int y = i / m.W, x = i - y * m.W;
-    const float g80 = norm80(g[i], gmin, gmax);
-    const float n80 = __fmul_rn(__fdiv_rn(__fadd_rn(gtn[i], 1.0f), 2.0f), 80.f);
-    bool valid = (n80 < 80.f) && (g80 < 80.f) && (n80 > 1.f) && (g80 > 1.f);
-    if (m.crop) valid = valid && (y >= m.cy1 && y < m.cy2 && x >= m.cx1 && x < m.cx2);
-    if (!valid) continue;
-    float vp = norm80(p[i], pmin, pmax);
+    float vg, vp;
+    if (!metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) continue;
     vp = __fdiv_rn(__fmul_rn(vp, med_g), med_p);
-    vp = fminf(fmaxf(vp, 1.f), 80.f);
-    const float vg = g80;
+    if (VAR == 0) vp = fminf(fmaxf(vp, 1.f), 80.f);       // :87
+    if (VAR == 1) vp = fminf(fmaxf(vp, 1e-3f), 10.f);     // :135
     const float thr = fmaxf(__fdiv_rn(vg, vp), __fdiv_rn(vp, vg));
     const float d = __fsub_rn(vg, vp);
     acc[0] += (double)fabsf(d);
     acc[1] += (double)__fdiv_rn(fabsf(d), vg);
-    acc[2] += (double)__fdiv_rn(__fmul_rn(d, d), vg);
+    if (VAR == 0) acc[2] += (double)__fdiv_rn(__fmul_rn(d, d), vg);
+    else acc[2] += (double)fabsf(__fsub_rn(log10f(vg), log10f(vp)));
     acc[3] += (thr < 1.25f) ? 1.0 : 0.0;
     acc[4] += (thr < 1.5625f) ? 1.0 : 0.0;
     acc[5] += (thr < 1.953125f) ? 1.0 : 0.0;
@@ -373,11 +408,13 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
     atomicAdd(m.out + 0, acc[0] / n * invB);
     atomicAdd(m.out + 1, acc[1] / n * invB);
     atomicAdd(m.out + 2, acc[2] / n * invB);
-    atomicAdd(m.out + 3, (double)((float)acc[3] / (float)nvalid) * invB);
-    atomicAdd(m.out + 4, (double)((float)acc[4] / (float)nvalid) * invB);
-    atomicAdd(m.out + 5, (double)((float)acc[5] / (float)nvalid) * invB);
+    if (VAR != 2) {
+      atomicAdd(m.out + 3, (double)((float)acc[3] / (float)nvalid) * invB);
+      atomicAdd(m.out + 4, (double)((float)acc[4] / (float)nvalid) * invB);
+      atomicAdd(m.out + 5, (double)((float)acc[5] / (float)nvalid) * invB);
+      atomicAdd(m.out + 7, sqrt(acc[7] / n) * invB);
+    }
     atomicAdd(m.out + 6, sqrt(acc[6] / n) * invB);
-    atomicAdd(m.out + 7, sqrt(acc[7] / n) * invB);
     if (m.counts) {
       m.counts[b * 4 + 0] = nvalid;
       m.counts[b * 4 + 1] = (long long)acc[3];
@@ -478,20 +515,33 @@ GDN_API int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* ou
   return GDN_OK;
 }
 
-GDN_API int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
-                              double* out8, int64_t* counts, gdn_stream stream) {
-  if (!gt_np || !gt || !pred || !out8 || b < 1) return fail(GDN_INVALID_DESC, "gdn_eigen_metrics: bad arguments");
+GDN_API int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, const float* pred, int b, int h, int w,
+                              int crop, double* out8, int64_t* counts, gdn_stream stream) {
+  if (variant < 0 || variant > 2) return fail(GDN_INVALID_DESC, "gdn_depth_metrics: variant %d", variant);
+  if ((!gt_np && variant != GDN_METRICS_NYU) || !gt || !pred || !out8 || b < 1)
+    return fail(GDN_INVALID_DESC, "gdn_depth_metrics: bad arguments");
   MetricK m{};
   m.gt_np = gt_np; m.gt = gt; m.pred = pred;
-  m.B = b; m.H = h; m.W = w; m.crop = crop;
-  // crop used by Godard CVPR17 (calculate_error.py:28-29)
-  m.cy1 = (int)(0.3324324 * h); m.cy2 = (int)(0.91351351 * h);
+  m.B = b; m.H = h; m.W = w; m.crop = (variant == GDN_METRICS_MAKE3D) ? 0 : crop;
+  if (variant == GDN_METRICS_KITTI) {
+    // crop used by Godard CVPR17 (calculate_error.py:28-29)
+    m.cy1 = (int)(0.3324324 * h); m.cy2 = (int)(0.91351351 * h);
+  } else {
+    m.cy1 = (int)(0.0359477 * h); m.cy2 = (int)(0.96405229 * h);   // calculate_error.py:111
+  }
   m.cx1 = (int)(0.0359477 * w); m.cx2 = (int)(0.96405229 * w);
   m.out = out8;
   m.counts = reinterpret_cast<long long*>(counts);
-  eigen_metrics_kernel<<<b, 1024, 0, (cudaStream_t)stream>>>(m);
+  if (variant == GDN_METRICS_KITTI) eigen_metrics_kernel<0><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
+  else if (variant == GDN_METRICS_NYU) eigen_metrics_kernel<1><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
+  else eigen_metrics_kernel<2><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
   GDN_LAUNCH_CHECK("eigen_metrics_kernel");
   return GDN_OK;
+}
+
+GDN_API int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
+                              double* out8, int64_t* counts, gdn_stream stream) {
+  return gdn_depth_metrics(GDN_METRICS_KITTI, gt_np, gt, pred, b, h, w, crop, out8, counts, stream);
 }
 
 GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

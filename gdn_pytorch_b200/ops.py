@@ -2,6 +2,7 @@
 
   compute_errors(gt_np, gt, pred, crop=True)   drop-in for calculate_error.compute_errors
                                                (/root/reference/src/calculate_error.py:10-103): list of 8 floats
+  compute_errors_NYU / compute_errors_Make3D   the other two evaluation protocols (:105-182), same kernel
   eigen_metrics_device(...)                    same numbers without the host sync (+ exact integer delta counts)
   LossKernels                                  RtoD / DtoD training loss with analytic gradient
                                                (/root/reference/src/trainer.py:433-456, 705-757)
@@ -54,6 +55,38 @@ def compute_errors(gt_np, gt, pred, crop=True):
     reference's per-image syncs)."""
     out8, _ = eigen_metrics_device(gt_np, gt, pred, crop)
     return out8.tolist()
+
+
+def _depth_metrics(variant, gt_np, gt, pred, crop):
+    gt, pred = _chk_map(gt, "gt"), _chk_map(pred, "pred")
+    B, H, W = gt.shape[0], gt.shape[-2], gt.shape[-1]
+    if gt.numel() != B * H * W or pred.numel() != B * H * W:
+        raise ValueError("gdn_b200 depth metrics expect single-channel (B,1,H,W) depth maps")
+    if gt_np is not None:
+        gt_np = _chk_map(gt_np, "gt_np")
+        if gt_np.numel() != B * H * W:
+            gt_np = gt_np[:, 0].contiguous()
+    out8 = torch.zeros(8, dtype=torch.float64, device=gt.device)
+    counts = torch.zeros((B, 4), dtype=torch.int64, device=gt.device)
+    L = _lib.lib()
+    with torch.cuda.device(gt.device):
+        rc = L.gdn_depth_metrics(variant, C.c_void_p(gt_np.data_ptr() if gt_np is not None else None),
+                                 C.c_void_p(gt.data_ptr()), C.c_void_p(pred.data_ptr()), B, H, W, int(bool(crop)),
+                                 C.c_void_p(out8.data_ptr()), C.c_void_p(counts.data_ptr()), _lib.stream_ptr())
+    _lib.check(rc, "depth_metrics")
+    return out8, counts
+
+
+def compute_errors_NYU(gt, pred, crop=True):
+    """drop-in for calculate_error.compute_errors_NYU (/root/reference/src/calculate_error.py:105-151):
+    [abs_diff, abs_rel, log10, a1, a2, a3, rmse, rmse_log] as Python floats"""
+    return _depth_metrics(1, None, gt, pred, crop)[0].tolist()
+
+
+def compute_errors_Make3D(gt_np, gt, pred):
+    """drop-in for calculate_error.compute_errors_Make3D (:153-182): [abs_diff, abs_rel, ave_log10, rmse]"""
+    o = _depth_metrics(2, gt_np, gt, pred, False)[0].tolist()
+    return [o[0], o[1], o[2], o[6]]
 
 
 # --------------------------------------------------------------------------------------------------- loss

@@ -145,6 +145,9 @@ class _StepBase:
                                  flat=(self.flat_params, eng.flat_grad))
         else:
             self.opt.flat = (self.flat_params, eng.flat_grad)
+        pend = self.__dict__.pop("_pending_opt_state", None)
+        if pend is not None:
+            self._apply_opt_state(pend)
         # bucket plan: a parameter's gradient is final after the last backward op that mentions it
         slots, o = [], 0
         for n, p in named:
@@ -234,6 +237,58 @@ class _StepBase:
                 st.copy_(t, non_blocking=True)
         self._graph.replay()
         return self._static_out
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to resume training exactly: the model's own state_dict (keys identical to the
+        reference's checkpoints, trainer.py:518,843 -- it can be loaded by the reference as is), the Adam moments
+        (flat, named_parameters order), the step count and the current learning rate.  The reference saves weights
+        only (no optimizer state, no resume flag: SURVEY.md section 5)."""
+        sd = {"model": {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+              "step": self._steps_taken(), "lr": float(self.lr),
+              "hyper": {"betas": tuple(self.hyper[0]), "eps": self.hyper[1], "weight_decay": self.hyper[2]}}
+        if self.opt is not None and self.opt._flat_state is not None:
+            sd["adam_m"], sd["adam_v"] = (t.detach().clone() for t in self.opt._flat_state)
+        return sd
+
+    def _steps_taken(self):
+        """optimizer steps so far (under graph replay the authoritative counter is the device-side one)"""
+        if self.opt is None:
+            return 0
+        if self.opt.dyn is not None:
+            return int(round(float(self.opt.dyn[1])))
+        return int(self.opt._step)
+
+    def load_state_dict(self, sd):
+        """inverse of state_dict(); parameters are copied IN PLACE (the flat buffer and every raw pointer the
+        engines hold stay valid), the CUDA graph keeps replaying with the restored step count / learning rate"""
+        self.model.load_state_dict(sd["model"])
+        self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1   # engines re-pack / re-fold
+        if self.eng is not None:
+            self.eng._wversion = None
+        self.lr = float(sd["lr"])
+        if self.opt is None:
+            self._pending_opt_state = sd       # applied when the optimizer is created by the first step
+            return
+        self._apply_opt_state(sd)
+
+    def _apply_opt_state(self, sd):
+        opt = self.opt
+        opt._step = int(sd["step"])
+        opt.set_lr(float(sd["lr"]))
+        if "adam_m" in sd:
+            if opt._flat_state is None:
+                opt._flat_state = (torch.zeros_like(self.flat_params), torch.zeros_like(self.flat_params))
+            opt._flat_state[0].copy_(sd["adam_m"])
+            opt._flat_state[1].copy_(sd["adam_v"])
+        if opt.dyn is not None:
+            opt.dyn[1:2].fill_(float(opt._step))
+
+    def save_checkpoint(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.dev))
 
     def _eager_on_main(self, inputs):
         """run the step on the high-priority stream, ordered after / before the caller's current stream"""

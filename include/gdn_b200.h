@@ -220,6 +220,18 @@ int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* out, gdn_s
 int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
                       double* out8, int64_t* counts, gdn_stream stream);
 
+/* The same kernel with the constants of the other two evaluation protocols of calculate_error.py:
+ *   GDN_METRICS_KITTI  = compute_errors        (:10-103)  = gdn_eigen_metrics
+ *   GDN_METRICS_NYU    = compute_errors_NYU    (:105-151): 10 m range, valid = 0 < gt < 10, border crop, clamp(1e-3, 10);
+ *                        out8 = [abs_diff, abs_rel, log10, a1, a2, a3, rmse, rmse_log]; gt_np unused (may be NULL)
+ *   GDN_METRICS_MAKE3D = compute_errors_Make3D (:153-182): min-max normalised gt_np / gt / pred, clamp(1e-2, 80) BEFORE
+ *                        the median scaling, no crop; out8 = [abs_diff, abs_rel, log10, 0, 0, 0, rmse, 0] */
+#define GDN_METRICS_KITTI 0
+#define GDN_METRICS_NYU 1
+#define GDN_METRICS_MAKE3D 2
+int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
+                      double* out8, int64_t* counts, gdn_stream stream);
+
 /* Fused Adam with coupled L2 decay over flat fp32 buffers (torch.optim.Adam semantics); step is 1-based;
  * the gradient is multiplied by grad_scale first. */
 int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

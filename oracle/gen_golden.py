@@ -10,6 +10,7 @@ What is recorded (all fp32, CPU, torch threads = default):
                                  (trainer.py is not importable; its arithmetic is replayed line by line here with
                                  the reference's own helpers and boolean-mask writes, see _ref_inline_*)
   metrics.npz                  : calculate_error.compute_errors on synthetic pred/gt
+  metrics_variants.npz         : calculate_error.compute_errors_NYU / compute_errors_Make3D on synthetic pred/gt
   trainstep_DtoD.npz           : one fwd+loss+bwd+Adam step of the reference AutoEncoder_DtoD at 2x1x32x64
 """
 import os
@@ -49,6 +50,20 @@ def _ref_inline_berhu(outputs, depths, sparse):
     diff_abs[~crop_mask] = 0.1 * diff_abs[~crop_mask]
     diff_abs[crop_mask & (~valid_mask)] = 0.3 * diff_abs[crop_mask & (~valid_mask)]
     return 3 * diff_abs.mean(), c
+
+
+def gen_metric_variants(ce):
+    """metrics_variants.npz: calculate_error.compute_errors_NYU / compute_errors_Make3D on synthetic pred / gt"""
+    rec = {}
+    for hh, ww, tag in ((128, 416, "kitti"), (48, 64, "small")):
+        pred = synth.synth_pred(3, hh, ww, 6)
+        gt = synth.synth_depth(3, hh, ww, 6)
+        gtn = synth.synth_sparse(gt, 6, keep=0.6)
+        rec["nyu_" + tag] = np.array(ce.compute_errors_NYU(gt.clone(), pred.clone(), crop=True), dtype=np.float64)
+        rec["nyu_nocrop_" + tag] = np.array(ce.compute_errors_NYU(gt.clone(), pred.clone(), crop=False), dtype=np.float64)
+        rec["make3d_" + tag] = np.array(ce.compute_errors_Make3D(gtn.clone(), gt.clone(), pred.clone()), dtype=np.float64)
+        print("metric variants", tag, rec["nyu_" + tag], rec["make3d_" + tag])
+    np.savez(os.path.join(OUT, "metrics_variants.npz"), **rec)
 
 
 def main():
@@ -122,6 +137,7 @@ def main():
         rec[tag] = np.array(res, dtype=np.float64)
         print("metrics", tag, res)
     np.savez(os.path.join(OUT, "metrics.npz"), **rec)
+    gen_metric_variants(ce)
 
     # ------------------------------------------------- one DtoD training step
     torch.manual_seed(0)

@@ -285,3 +285,33 @@ def test_fused_adam_matches_torch_adam():
         ob.step()
     for x, y in zip(a, b):
         assert torch.allclose(x, y, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 416), (3, 48, 64), (2, 480, 640)])
+def test_nyu_and_make3d_metric_variants(shape):
+    """calculate_error.compute_errors_NYU / _Make3D: delta counts bit-exact vs the oracle, continuous metrics 0.5 %,
+    and the reference's own numbers (tests/golden/metrics_variants.npz) where a golden shape exists"""
+    from gdn_pytorch_b200 import ops
+    from oracle import metrics as OMet, synth
+    from tests.util import golden
+    B, H, W = shape
+    pred, gt = synth.synth_pred(B, H, W, 6), synth.synth_depth(B, H, W, 6)
+    gtn = synth.synth_sparse(gt, 6, keep=0.6)
+    for crop in (True, False):
+        out8, counts = ops._depth_metrics(1, None, gt.to(dev), pred.to(dev), crop)
+        r8, rc = OMet.nyu_metrics(gt, pred, crop)
+        assert torch.equal(counts.cpu(), rc)
+        for a, b in zip(out8.tolist(), r8):
+            assert abs(a - b) <= 5e-3 * abs(b)
+    m4 = ops.compute_errors_Make3D(gtn.to(dev), gt.to(dev), pred.to(dev))
+    r4, nv = OMet.make3d_metrics(gtn, gt, pred)
+    _, counts = ops._depth_metrics(2, gtn.to(dev), gt.to(dev), pred.to(dev), False)
+    assert counts[:, 0].cpu().tolist() == nv.tolist()
+    for a, b in zip(m4, r4):
+        assert abs(a - b) <= 5e-3 * abs(b)
+    tag = {(3, 128, 416): "kitti", (3, 48, 64): "small"}.get(shape)
+    if tag:
+        gold = golden("metrics_variants.npz")
+        got = ops.compute_errors_NYU(gt.to(dev), pred.to(dev), crop=True)
+        assert np.allclose(got, gold["nyu_" + tag], rtol=5e-3)
+        assert np.allclose(m4, gold["make3d_" + tag], rtol=5e-3)

@@ -139,3 +139,15 @@ def test_oracle_live_against_reference():
     r1 = ce.compute_errors(gtn, gt, pred, crop=True)
     r2, _ = OMet.eigen_metrics(gtn, gt, pred, crop=True)
     np.testing.assert_allclose(np.array(r1), np.array(r2), rtol=2e-6)
+
+
+def test_metric_variants_match_reference_golden():
+    """compute_errors_NYU / compute_errors_Make3D restatements against the reference's own outputs"""
+    gold = golden("metrics_variants.npz")
+    for hh, ww, tag in ((128, 416, "kitti"), (48, 64, "small")):
+        pred = synth.synth_pred(3, hh, ww, 6)
+        gt = synth.synth_depth(3, hh, ww, 6)
+        gtn = synth.synth_sparse(gt, 6, keep=0.6)
+        np.testing.assert_allclose(np.array(OMet.nyu_metrics(gt, pred, True)[0]), gold["nyu_" + tag], rtol=5e-6)
+        np.testing.assert_allclose(np.array(OMet.nyu_metrics(gt, pred, False)[0]), gold["nyu_nocrop_" + tag], rtol=5e-6)
+        np.testing.assert_allclose(np.array(OMet.make3d_metrics(gtn, gt, pred)[0]), gold["make3d_" + tag], rtol=5e-6)
