@@ -184,6 +184,15 @@ int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const float* scale
                       int* n_ctas);
 int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int max_taps, gdn_stream stream);
 
+/* ---- device-side input pipeline (the reference's per-sample CPU transforms) ----------------
+ * src: uint8 [n][h][w][c] (HWC, as decoded); dst: fp32 [n][c][h][w] in [-1, 1] = Normalize(0.5, 0.5)(ArrayToTensor(.)),
+ * transform_list.py:84-113.  flip[n] != 0 mirrors sample n horizontally (RandomHorizontalFlip, :161-169); crop[n] =
+ * (scaled_h, scaled_w, off_y, off_x) zooms sample n to scaled_h x scaled_w (bilinear, rounded to uint8) and keeps
+ * the h x w window at the offset (RandomScaleCrop, :189-203).  Both may be NULL.  The random draws stay on the host
+ * (gdn_pytorch_b200/data.py replays the reference's RNG calls). */
+int gdn_preprocess_u8(const uint8_t* src, float* dst, int n, int h, int w, int c, const int32_t* flip, const float* crop,
+                      gdn_stream stream);
+
 /* ---- training loss, metrics, optimizer ------------------------------------------------------------------ */
 
 /* out_max[0] = max(out_max[0], max_i |a[i] - b[i]|)  (caller zeroes; non-negative float compared as bits).

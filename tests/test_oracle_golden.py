@@ -151,3 +151,32 @@ def test_metric_variants_match_reference_golden():
         np.testing.assert_allclose(np.array(OMet.nyu_metrics(gt, pred, True)[0]), gold["nyu_" + tag], rtol=5e-6)
         np.testing.assert_allclose(np.array(OMet.nyu_metrics(gt, pred, False)[0]), gold["nyu_nocrop_" + tag], rtol=5e-6)
         np.testing.assert_allclose(np.array(OMet.make3d_metrics(gtn, gt, pred)[0]), gold["make3d_" + tag], rtol=5e-6)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_transform_restatement_matches_reference_classes():
+    """oracle/transforms.py against the reference's own ArrayToTensor / Normalize / RandomHorizontalFlip classes
+    (transform_list.py imported with scipy.misc stubbed: imresize no longer exists, so RandomScaleCrop cannot run)"""
+    import importlib.util
+    import random
+    import sys
+    import types
+    from oracle import transforms as OT
+    if "scipy.misc" not in sys.modules or not hasattr(sys.modules["scipy.misc"], "imresize"):
+        m = types.ModuleType("scipy.misc")
+        m.imresize = m.imrotate = None
+        sys.modules["scipy.misc"] = m
+    spec = importlib.util.spec_from_file_location("_gdn_reference_transform_list", "/root/reference/src/transform_list.py")
+    tl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tl)
+    rs = np.random.RandomState(0)
+    h, w = 32, 64
+    gt = rs.randint(0, 256, (h, w)).astype(np.float32)          # load_as_float yields float arrays of 0..255
+    rgb = rs.randint(0, 256, (h, w, 3)).astype(np.float32)
+    pipe = tl.Compose([tl.ArrayToTensor(height=h, width=w), tl.Normalize(mean=[0.5, 0.5, 0.5], std=[0.5, 0.5, 0.5])])
+    ref = pipe([gt.copy(), rgb.copy()])
+    assert torch.equal(ref[0], OT.to_tensor_normalize(gt.astype(np.uint8)))
+    assert torch.equal(ref[1], OT.to_tensor_normalize(rgb.astype(np.uint8)))
+    random.seed(1)                                               # first draw 0.134 < 0.5 -> flips
+    flipped = tl.RandomHorizontalFlip()([rgb.copy()])[0]
+    assert np.array_equal(flipped.astype(np.uint8), OT.flip_scale_crop(rgb.astype(np.uint8), True, None))
