@@ -665,7 +665,8 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
     k.J = J;
     k.halo_w = halo_w;
     k.a_bytes = (uint32_t)halo_h * halo_w * 128;
-    k.na = (k.chunks0 > 1 && 2 * (size_t)k.a_bytes + 3 * b_bytes <= smem_budget) ? 2 : 1;
+    // two halo buffers whenever they fit: with one 64-channel chunk the second buffer prefetches the NEXT tile's halo
+    k.na = (2 * (size_t)k.a_bytes + 3 * b_bytes <= smem_budget) ? 2 : 1;
     size_t rem = smem_budget - (size_t)k.na * k.a_bytes;
     k.nbst = (int)(rem / b_bytes);
     if (k.nbst > kMaxB) k.nbst = kMaxB;
