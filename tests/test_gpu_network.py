@@ -412,3 +412,25 @@ def test_checkpoint_resume_restores_model_optimizer_and_step(tmp_path):
     cos = (torch.dot(ma, mb) / (ma.norm() * mb.norm())).item()
     assert 0.8 <= ratio <= 1.25 and cos >= 0.5, (ratio, cos)   # chaotic train-mode DtoD at 32x64: see tools/check_repro.py
     assert float(b.opt.dyn[1]) == 6.0
+
+
+def test_device_validator_matches_the_reference_loop():
+    """trainer.py:17-87 restated with the oracle (per-batch compute_errors -> AverageMeter) vs the sync-free validator"""
+    from gdn_pytorch_b200.validate import DeviceValidator
+    from oracle import model as OM, metrics as OMet, synth
+    m, sd = _module("AutoEncoder_2", seed=2)
+    m.eval()
+    val = DeviceValidator(m, mode="RtoD", dataset="KITTI")
+    ref_rows = []
+    for i in range(3):
+        rgb, gt = synth.synth_rgb(B, H, W, 10 + i), synth.synth_depth(B, H, W, 10 + i)
+        gtn = synth.synth_sparse(gt, 10 + i, keep=0.7)
+        out = val.update(gt.to(dev), rgb.to(dev), gtn.to(dev))
+        ref_rows.append(OMet.eigen_metrics(gtn, gt, out.cpu(), crop=True)[0])     # metrics of the SAME prediction
+    avg, mins, names = val.result()
+    assert names[0] == "abs_diff" and len(avg) == 8 and len(mins) == 8
+    want = [sum(r[c] for r in ref_rows) / 3 for c in range(8)]
+    for a, b in zip(avg, want):
+        assert abs(a - b) <= 5e-3 * abs(b) + 1e-9
+    for a, b in zip(mins, want):
+        assert abs(a - b) <= 5e-3 * abs(b) + 1e-9
