@@ -946,6 +946,69 @@ __global__ void __launch_bounds__(kEwThreads) fold_rows_kernel(const FoldK f, co
   }
 }
 
+// ---- backward through a FROZEN (eval-mode, BatchNorm folded) unit: dy = g * [y > 0] * scale[c] as bf16.
+// y is the unit's own post-ReLU output (fp32 stream or plain bf16 buffer); the folded BatchNorm scale is applied to the
+// gradient here so that the input-gradient convolution can use the un-folded weight pack.
+struct FrozenBwd {
+  const float* dact;
+  const float* y_f32;
+  const __nv_bfloat16* y_bf16;
+  const float* scale;
+  int relu, C;
+  long long items;   // n*h*w*C/8
+  __nv_bfloat16* dy;
+};
+
+__global__ void __launch_bounds__(kEwThreads) frozen_bwd_kernel(const FrozenBwd b) {
+  const int cg = b.C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.items; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg) * 8;
+    const size_t off = (size_t)i * 8;
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(b.dact + off));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(b.dact + off + 4));
+    float g[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    if (b.relu) {
+      float y[8];
+      if (b.y_f32) {
+        const float4 y0 = __ldg(reinterpret_cast<const float4*>(b.y_f32 + off));
+        const float4 y1 = __ldg(reinterpret_cast<const float4*>(b.y_f32 + off + 4));
+        y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+      } else {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b.y_bf16 + off)), y);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (!(y[j] > 0.f)) g[j] = 0.f;
+    }
+    if (b.scale) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) g[j] *= __ldg(b.scale + c8 + j);
+    }
+    *reinterpret_cast<uint4*>(b.dy + off) = pack8(g);
+  }
+}
+
+// adjoint of reflection padding for thin (C not a multiple of 4) tensors: the input gradient of a first layer
+__global__ void fold_thin_kernel(const FoldK f) {
+  const int Hq = f.H + 2 * f.P, Wq = f.W + 2 * f.P;
+  const long long total = (long long)f.N * f.H * f.W * f.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % f.C);
+    long long t = i / f.C;
+    const int x = (int)(t % f.W);
+    t /= f.W;
+    const int y = (int)(t % f.H);
+    const long long n = t / f.H;
+    int my[3], mx[3];
+    const int cy = mirror_set(y, f.H, f.P, f.reflect, my);
+    const int cx = mirror_set(x, f.W, f.P, f.reflect, mx);
+    float acc = f.accumulate ? f.dact[i] : 0.f;
+    for (int p = 0; p < cy; p++)
+      for (int q = 0; q < cx; q++) acc += f.dpad[((n * Hq + my[p]) * Wq + mx[q]) * f.ctot + f.c_off + c];
+    f.dact[i] = acc;
+  }
+}
+
 // -------------------------------------------------------------------------------- weight pack / unpack
 // packed[t][a][b] (t = r*kw + s, a < A, b < B) <-> w[a*sa + b*sb + r'*sr + s'*ss], (r', s') flipped when flip.
 // For im2col'd layers (col_c > 0): packed[0][a][k], k = (r*kw + s)*col_c + c  <->  w[a*sa + c*sb + r*sr + s*ss].
@@ -1301,13 +1364,21 @@ GDN_API int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream) {
 
 GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
   if (!d || !d->dpad || !d->dact) return fail(GDN_INVALID_DESC, "gdn_fold_grad: null pointer");
-  if (d->c % 4 || d->ctot % 4 || d->c_off % 4) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: channel alignment");
+  const bool thin = (d->c % 4 || d->ctot % 4 || d->c_off % 4);
+  if (thin && (d->up || d->dilate))
+    return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: channel alignment (thin tensors: reflection / zero padding only)");
   if (d->up > 1) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: only the align_corners=False adjoint is implemented");
+  if (d->reflect && (d->pad >= d->h || d->pad >= d->w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: reflection pad too large");
   FoldK f{};
   f.dpad = d->dpad; f.ctot = d->ctot; f.c_off = d->c_off;
   f.N = d->n; f.H = d->h; f.W = d->w; f.C = d->c;
   f.P = d->pad; f.reflect = d->reflect; f.up = d->up; f.dilate = d->dilate;
   f.dact = d->dact; f.accumulate = d->accumulate;
+  if (thin) {
+    fold_thin_kernel<<<ew_grid((long long)f.N * f.H * f.W * f.C), kEwThreads, 0, (cudaStream_t)stream>>>(f);
+    GDN_LAUNCH_CHECK("fold_thin_kernel");
+    return GDN_OK;
+  }
   {
     const int lg = ew_lg2(f.C / 4);
     if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
@@ -1320,6 +1391,21 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
   const long long work = (long long)f.N * f.H * f.W * (f.C / 4);
   fold_grad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(f);
   GDN_LAUNCH_CHECK("fold_grad_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_act_backward_frozen(const gdn_frozen_bwd_desc* d, gdn_stream stream) {
+  if (!d || !d->dact || !d->dy) return fail(GDN_INVALID_DESC, "gdn_act_backward_frozen: null pointer");
+  if (d->relu && !d->y_f32 && !d->y_bf16) return fail(GDN_INVALID_DESC, "gdn_act_backward_frozen: ReLU needs the unit's output");
+  if (d->c % 8) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_act_backward_frozen: channels %d (need a multiple of 8)", d->c);
+  FrozenBwd b{};
+  b.dact = d->dact; b.y_f32 = d->y_f32; b.y_bf16 = (const __nv_bfloat16*)d->y_bf16; b.scale = d->scale;
+  b.relu = d->relu; b.C = d->c;
+  b.items = (long long)d->n * d->h * d->w * (d->c / 8);
+  b.dy = (__nv_bfloat16*)d->dy;
+  if (b.items == 0) return GDN_OK;
+  frozen_bwd_kernel<<<ew_grid(b.items), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+  GDN_LAUNCH_CHECK("frozen_bwd_kernel");
   return GDN_OK;
 }
 

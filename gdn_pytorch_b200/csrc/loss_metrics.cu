@@ -223,6 +223,26 @@ __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __re
   if (threadIdx.x == 0) atomicAdd(out, acc[0]);
 }
 
+// ------------------------------------------------- guidance-loss gradient (opt-in)
+// g[i] = coef * (a[i] - b[i]): gradient of coef/2 * sum (a - b)^2 w.r.t. a (one feature-MSE term of the latent loss)
+__global__ void sqdiff_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float coef,
+                                   float* __restrict__ g) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(g)[i] = make_float4(coef * (x.x - y.x), coef * (x.y - y.y), coef * (x.z - y.z), coef * (x.w - y.w));
+  }
+}
+
+// dpre[i] += scale * dout[i] * (1 - out[i]^2): chains a gradient w.r.t. the tanh output onto dL/d(pre-tanh)
+__global__ void tanh_chain_add_kernel(const float* __restrict__ dout, const float* __restrict__ out, long long n, float scale,
+                                      float* __restrict__ dpre) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = out[i];
+    dpre[i] += scale * dout[i] * (1.f - o * o);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- depth metrics
 // One block per image.  Arithmetic follows calculate_error.py operation by operation in fp32.
 //   VAR 0  compute_errors        (KITTI / Eigen, :10-103)   out8 = abs_diff abs_rel sq_rel a1 a2 a3 rmse rmse_log
@@ -512,6 +532,20 @@ GDN_API int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* ou
   if (!a || !b || !out || (n & 3)) return fail(GDN_INVALID_DESC, "gdn_sqdiff_sum: bad arguments (n must be a multiple of 4)");
   sqdiff_sum_kernel<<<lm_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, out);
   GDN_LAUNCH_CHECK("sqdiff_sum_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_sqdiff_grad(const float* a, const float* b, int64_t n, float coef, float* grad, gdn_stream stream) {
+  if (!a || !b || !grad || (n & 3)) return fail(GDN_INVALID_DESC, "gdn_sqdiff_grad: bad arguments (n must be a multiple of 4)");
+  sqdiff_grad_kernel<<<lm_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, coef, grad);
+  GDN_LAUNCH_CHECK("sqdiff_grad_kernel");
+  return GDN_OK;
+}
+
+GDN_API int gdn_tanh_chain_add(const float* dout, const float* out, int64_t n, float scale, float* dpre, gdn_stream stream) {
+  if (!dout || !out || !dpre || n < 0) return fail(GDN_INVALID_DESC, "gdn_tanh_chain_add: bad arguments");
+  tanh_chain_add_kernel<<<lm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, n, scale, dpre);
+  GDN_LAUNCH_CHECK("tanh_chain_add_kernel");
   return GDN_OK;
 }
 

@@ -42,6 +42,12 @@ class BnBwdDesc(C.Structure):
                 ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("raw_is_half", C.c_int32)]
 
 
+class FrozenBwdDesc(C.Structure):
+    _fields_ = [("dact", C.c_void_p), ("y_f32", C.c_void_p), ("y_bf16", C.c_void_p), ("scale", C.c_void_p),
+                ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("dy", C.c_void_p)]
+
+
 class FoldDesc(C.Structure):
     _fields_ = [("dpad", C.c_void_p), ("ctot", C.c_int32), ("c_off", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("c", C.c_int32), ("pad", C.c_int32), ("reflect", C.c_int32), ("up", C.c_int32),
@@ -69,13 +75,18 @@ class _U:
 
 class Engine:
     def __init__(self, graph: Graph, params: dict, N: int, H: int, W: int, train: bool, backward: bool = False,
-                 want=(), stop_after: str = None, device=None, input_grad: bool = False):
+                 want=(), stop_after: str = None, device=None, input_grad: bool = False, grad_seeds=()):
         """params: state_dict-like mapping (no 'module.' prefix) to the module's OWN cuda fp32 tensors
         (parameters are read in place, BN running statistics are updated in place in train mode).
-        want: tensor names whose fp32 NHWC value must be available after forward()."""
+        want: tensor names whose fp32 NHWC value must be available after forward().
+        backward with train=False builds the FROZEN backward plan (activation gradients only, BatchNorm folded, no
+        parameter gradients): the caller writes dL/d(t) into ``dact[t]`` for every t in grad_seeds, run_backward()
+        propagates them (input_grad=True: down to ``dact["in"]``, also for thin 1-channel inputs)."""
         self.L = _lib.lib()
         self.g, self.P, self.N, self.H, self.W = graph, params, N, H, W
         self.train, self.do_bwd = train, backward
+        self.frozen_bwd = backward and not train
+        self.input_grad, self.grad_seeds = bool(input_grad), tuple(grad_seeds)
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.want = set(want)
         units = []
@@ -90,14 +101,17 @@ class Engine:
         # dgrad -> BatchNorm-backward -> dgrad chain, so its tensor-core kernels overlap the HBM-bound elementwise
         # kernels of the main chain (they co-reside on an SM: the elementwise CTAs need no shared memory)
         self.side_stream = None
-        if backward and os.environ.get("GDN_SIDE", "1") != "0":
+        if backward and train and os.environ.get("GDN_SIDE", "1") != "0":
             self.side_stream = torch.cuda.Stream(device=self.dev, priority=-1)
         self._infer_shapes()
         self._plan_tensors()
         self._alloc()
         self._build_forward()
         if backward:
-            self._build_backward()
+            if train:
+                self._build_backward()
+            else:
+                self._build_backward_frozen()
         if os.environ.get("GDN_PACK_TABLE", "1") != "0":
             self.pack_ops = self._batch_packs(self.pack_ops)
             if backward:
@@ -159,6 +173,9 @@ class Engine:
         # network heads have no bf16 consumers; their value is the fp32 output
         for u in self.units:
             if u.tanh:
+                self.need_f32[u.out] = True
+            # frozen backward reads the ReLU mask from the unit's own output: plain bf16 buffer or the fp32 copy
+            if self.frozen_bwd and u.relu and (0, 0, 0, 0) not in self.variants[u.out]:
                 self.need_f32[u.out] = True
 
     # ------------------------------------------------------------------ buffers
@@ -679,6 +696,77 @@ class Engine:
             self.bwd[pos:pos] = side_ops
             self.grad_ready_op[u.conv + ".weight"] = pos + len(side_ops) - 1
 
+    def _build_backward_frozen(self):
+        """Backward plan of an eval-mode (frozen) network: activation gradients only.  Per unit, in reverse order:
+        residual identity, dy = g * [y > 0] * folded-BatchNorm scale (gdn_act_backward_frozen), then the same
+        input-gradient convolutions as in training, on the UN-folded weight packs (the scale went into dy).
+        Used by the opt-in guidance gradient (trainer.RtoDTrainStep(guidance_grad=True)): the
+        latent loss back-propagates through the frozen DtoD encoder into the RtoD output; the published
+        trainer.py:699-703 blocks that path with no_grad."""
+        L, N, dev = self.L, self.N, self.dev
+        self.bwd, self.pack_ops_bwd, self.grad_ready_op = [], [], {}
+        self.launches_bwd = 0
+        self.dact = {}
+        for t in self.shape:
+            if t == "in" and not self.input_grad:
+                continue
+            c, h, w = self.shape[t]
+            self.dact[t] = torch.zeros((N, h, w, c), dtype=torch.float32, device=dev)
+        self._pending_add = {}
+        have = set(self.grad_seeds)
+        for t in have:
+            if t not in self.shape:
+                raise ValueError("gdn_b200: gradient seed %r is not a tensor of this graph" % t)
+
+        def accumulate_flag(t):
+            f = t in have
+            have.add(t)
+            return f
+
+        for u in reversed(self.units):
+            cu = self.cu[u.conv]
+            if u.out not in have:
+                continue
+            if u.tanh or u.up or (u.relu and u.resid):
+                raise NotImplementedError("gdn_b200: frozen backward covers encoder-style units only (%s)" % u.conv)
+            ho, wo = cu.ho, cu.wo
+            g_out = self.dact[u.out]
+            if u.resid and u.resid not in have and self._next_grad_is_direct_conv(u):
+                self._pending_add[u.resid] = g_out
+                have.add(u.resid)
+            elif u.resid:
+                acc = accumulate_flag(u.resid)
+                a = ActFwdDesc()
+                a.src_f32 = g_out.data_ptr()
+                a.resid = self.dact[u.resid].data_ptr() if acc else None
+                a.n, a.h, a.w, a.c = N, ho, wo, u.cout
+                a.out_f32 = self.dact[u.resid].data_ptr()
+                self.bwd.append(self._call(L.gdn_act_forward, a, "resid-grad " + u.conv))
+                self.launches_bwd += 1
+            cu.dy = torch.empty((N, ho, wo, u.cout), dtype=torch.bfloat16, device=dev)
+            fb = FrozenBwdDesc()
+            fb.dact = g_out.data_ptr()
+            fb.relu = int(u.relu)
+            if u.relu:
+                if u.out in self.f32:
+                    fb.y_f32 = self.f32[u.out].data_ptr()
+                else:
+                    fb.y_bf16 = self.act[(u.out, (0, 0, 0, 0))].data_ptr()
+            fb.scale = cu.fold_scale.data_ptr() if u.bn is not None else None
+            fb.n, fb.h, fb.w, fb.c = N, ho, wo, u.cout
+            fb.dy = cu.dy.data_ptr()
+            self.bwd.append(self._call(L.gdn_act_backward_frozen, fb, "act_backward_frozen " + u.conv))
+            self.launches_bwd += 1
+            c_off = 0
+            self._dgrad_conv_end = len(self.bwd)
+            for s_name in u.srcs:
+                cs = self.shape[s_name][0]
+                if s_name == "in" and not self.input_grad:
+                    c_off += cs
+                    continue
+                self._build_dgrad(u, cu, s_name, c_off, cs, accumulate_flag(s_name))
+                c_off += cs
+
     def _next_grad_is_direct_conv(self, u):
         """True when the consumer of u.resid that runs next in backward order (the one closest before u in forward
         order) is a single-source, stride-1, zero-padded convolution -- its dgrad writes d(resid) directly."""
@@ -701,19 +789,20 @@ class Engine:
         if (not u.transposed) and u.stride == 2:
             self._build_dgrad_stride2(u, cu, s_name, c_off, cs, acc)
             return
-        wdg = torch.empty((kk, cs, u.cout), dtype=torch.bfloat16, device=dev)
+        cs_pad = 16 if cs < 16 else cs      # thin network input (frozen backward with input_grad): 16-wide MMA tile
+        wdg = torch.empty((kk, cs_pad, u.cout), dtype=torch.bfloat16, device=dev)
         if u.transposed:
             # w is (cin, cout, k, k): dX = conv(dy, w) -- no flip
-            pd = PackDesc(k, k, cs, u.cout, cs, u.cout, u.cout * kk, kk, k, 1, 0, 0)
+            pd = PackDesc(k, k, cs, u.cout, cs_pad, u.cout, u.cout * kk, kk, k, 1, 0, 0)
             w_off = c_off * u.cout * kk
         else:
-            pd = PackDesc(k, k, cs, u.cout, cs, u.cout, kk, u.cin * kk, k, 1, 1, 0)
+            pd = PackDesc(k, k, cs, u.cout, cs_pad, u.cout, kk, u.cin * kk, k, 1, 1, 0)
             w_off = c_off * kk
         self.pack_ops_bwd.append(self._pack_call(pd, wt, None, wdg, "pack-dgrad " + u.conv, w_off))
         d = ConvDesc()
         d.weights = wdg.data_ptr()
         d.kh = d.kw = k
-        d.cout = d.cout_pad = cs
+        d.cout, d.cout_pad = cs, cs_pad
         d.algo = 0
         d.dst_sy = d.dst_sx = 1
         direct = (not up) and (not refl) and (not dil)

@@ -135,6 +135,22 @@ class LossKernels:
                                        C.c_void_p(self.terms.data_ptr() + 8 * (3 + i)), _lib.stream_ptr())
             _lib.check(rc, "sqdiff_sum")
 
+    def latent_grad(self, feats, feats_tar, grads):
+        """opt-in guidance gradient: grads[i] <- d latent_loss / d feats[i]
+        = 1.5/4 * w_i * 2/numel_i * (feats[i] - feats_tar[i])  (latent_loss of trainer.py:726-733 WITHOUT the
+        no_grad of :699-703)"""
+        for w, a, b, g in zip(self.LATENT_W, feats, feats_tar, grads):
+            coef = 1.5 / 4.0 * w * 2.0 / float(a.numel())
+            rc = self.L.gdn_sqdiff_grad(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_int64(a.numel()),
+                                        C.c_float(coef), C.c_void_p(g.data_ptr()), _lib.stream_ptr())
+            _lib.check(rc, "sqdiff_grad")
+
+    def tanh_chain_add(self, dout, out, dpre, scale=1.0):
+        """dpre += scale * dout * (1 - out^2): add a gradient w.r.t. the network output to dL/d(pre-tanh)"""
+        rc = self.L.gdn_tanh_chain_add(C.c_void_p(dout.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(out.numel()),
+                                       C.c_float(scale), C.c_void_p(dpre.data_ptr()), _lib.stream_ptr())
+        _lib.check(rc, "tanh_chain_add")
+
     def assemble(self, mode, npix, feat_numels=None):
         """device-side scalar assembly (tiny fp64 tensor ops, no sync) -> dict of 0-dim tensors"""
         t = self.terms

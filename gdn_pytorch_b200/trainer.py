@@ -340,10 +340,15 @@ class RtoDTrainStep(_StepBase):
     """one iteration of train_AE_RtoD (trainer.py:670-768) with a frozen, eval-mode DtoD guidance network"""
 
     def __init__(self, model, dtod_model, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4, group=None,
-                 bucket_mb=25, guidance=True):
+                 bucket_mb=25, guidance=True, guidance_grad=False):
+        """guidance_grad=False (default) reproduces the published code: the latent loss is a reported constant
+        (both DtoD passes run under no_grad, trainer.py:699-703).  guidance_grad=True is the paper-faithful opt-in
+        (SURVEY.md 8f row 3): the latent loss back-propagates through the frozen DtoD encoder into the RtoD output
+        (input gradients of the DtoD encoder only -- its weights stay frozen) and on through the RtoD network."""
         super().__init__(model, lr, betas, eps, weight_decay, group, bucket_mb)
         self.dtod = dtod_model
         self.guidance = guidance and dtod_model is not None
+        self.guidance_grad = bool(guidance_grad) and self.guidance
         self.aux_stream = None
         if self.guidance:
             self.dtod.eval()
@@ -362,8 +367,9 @@ class RtoDTrainStep(_StepBase):
             from .engine import Engine
             from .module_runtime import _params
             names = self.dgraph.encoder_outputs
-            e = Engine(self.dgraph, _params(self.dtod), x.shape[0], x.shape[2], x.shape[3], train=False, backward=False,
-                       want=names, stop_after=names[-1], device=x.device)
+            gg = self.guidance_grad and slot == 1     # the prediction pass carries the guidance gradient
+            e = Engine(self.dgraph, _params(self.dtod), x.shape[0], x.shape[2], x.shape[3], train=False, backward=gg,
+                       want=names, stop_after=names[-1], device=x.device, input_grad=gg, grad_seeds=names if gg else ())
             self.deng[slot] = e
         e.forward(x)
         return [e.value(n) for n in self.dgraph.encoder_outputs]
@@ -390,7 +396,22 @@ class RtoDTrainStep(_StepBase):
         if self.world > 1:
             dist.all_reduce(self.kern.maxabs, op=dist.ReduceOp.MAX, group=self.group)
         self.kern.loss(0, out, depths, sparse, rgb, dpre=eng.dpre)
-        if self.guidance and ft_tar is None:
+        if self.guidance_grad:
+            # paper-faithful opt-in: d latent / d out through the frozen DtoD encoder, chained onto dL/d(pre-tanh)
+            # before the RtoD backward starts (so this pass IS on the critical chain, on the main stream)
+            if ft_tar is None:
+                ft_tar = self._dtod_features(0, depths)
+            else:
+                main.wait_stream(self.aux_stream)
+            ft = self._dtod_features(1, out)
+            self.kern.latent(ft, ft_tar)
+            feat_numels = [float(t.numel()) for t in ft]
+            e = self.deng[1]
+            e.refresh_if_stale()
+            self.kern.latent_grad(ft, ft_tar, [e.dact[n] for n in self.dgraph.encoder_outputs])
+            e.run_backward()
+            self.kern.tanh_chain_add(e.dact["in"], out, eng.dpre)
+        elif self.guidance and ft_tar is None:
             with torch.no_grad():
                 ft_tar = self._dtod_features(0, depths)
                 ft = self._dtod_features(1, out)

@@ -150,9 +150,25 @@ typedef struct {
 int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream);
 int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream);
 
+/* Backward through a FROZEN unit (eval mode, BatchNorm folded into the weights): dy = dact * [y > 0] * scale[c] as
+ * bf16, y = the unit's own post-ReLU output (fp32 NHWC or plain bf16 NHWC; exactly one when relu).  Opt-in
+ * guidance gradient through the frozen DtoD encoder (the published trainer.py:699-703 blocks it
+ * with no_grad).  No statistics, no parameter gradients. */
+typedef struct {
+  const float* dact;
+  const float* y_f32;
+  const void* y_bf16;
+  const float* scale;     /* folded BatchNorm scale per channel, or NULL */
+  int32_t relu;
+  int32_t n, h, w, c;
+  void* dy;
+} gdn_frozen_bwd_desc;
+int gdn_act_backward_frozen(const gdn_frozen_bwd_desc* d, gdn_stream stream);
+
 /* adjoint of the input transform of a conv: dpad is the fp32 gradient w.r.t. the conv's (padded / upsampled /
  * dilated) input buffer [n][OH + 2*pad][OW + 2*pad][ctot]; channels [c_off, c_off + c) are folded back onto the
- * source activation gradient dact [n][h][w][c] (+= when accumulate). */
+ * source activation gradient dact [n][h][w][c] (+= when accumulate).  Channel counts that are not multiples of 4
+ * (the 1- / 3-channel network input) are supported for reflection / zero padding only. */
 typedef struct {
   const float* dpad;
   int32_t ctot, c_off;
@@ -222,6 +238,12 @@ int gdn_loss(const gdn_loss_desc* d, gdn_stream stream);
 
 /* out[0] += sum_i (a[i] - b[i])^2   (feature MSE of the guidance loss, trainer.py:726-733); n % 4 == 0 */
 int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* out, gdn_stream stream);
+
+/* grad[i] = coef * (a[i] - b[i])  -- d/da of (coef/2) * sum (a - b)^2: one feature term of the latent (guidance) loss
+ * when its gradient is enabled; n % 4 == 0 */
+int gdn_sqdiff_grad(const float* a, const float* b, int64_t n, float coef, float* grad, gdn_stream stream);
+/* dpre[i] += scale * dout[i] * (1 - out[i]^2): adds a gradient w.r.t. the network's tanh output to dL/d(pre-tanh) */
+int gdn_tanh_chain_add(const float* dout, const float* out, int64_t n, float scale, float* dpre, gdn_stream stream);
 
 /* calculate_error.compute_errors (calculate_error.py:10-103), one CTA per image, exact lower medians by radix
  * select.  out8 += [abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log] averaged over the b images (caller

@@ -79,19 +79,21 @@ def dtod_loss(outputs, depths, sparse):
 LATENT_W = (1.0, 2.5, 14.0, 12.0)
 
 
-def latent_loss(feats, feats_tar):
-    """trainer.py:726-733; both feature sets come from no_grad DtoD passes (:699-703) -> constant."""
+def latent_loss(feats, feats_tar, with_grad=False):
+    """trainer.py:726-733; both feature sets come from no_grad DtoD passes (:699-703) -> constant.
+    with_grad=True keeps the graph of the prediction features: the paper-faithful opt-in of SURVEY.md 8f row 3
+    (what the published code would compute without the no_grad around :702-703); targets stay detached."""
     tot = 0.0
     for w, f, t in zip(LATENT_W, feats, feats_tar):
-        tot = tot + w * F.mse_loss(f.detach(), t.detach())
+        tot = tot + w * F.mse_loss(f if with_grad else f.detach(), t.detach())
     return 1.5 * (tot / 4)
 
 
-def rtod_loss(outputs, depths, sparse, rgb, feats=None, feats_tar=None):
+def rtod_loss(outputs, depths, sparse, rgb, feats=None, feats_tar=None, guidance_grad=False):
     """RtoD step loss, trainer.py:705-757.  feats/feats_tar: 4 DtoD feature maps each (or None = RtoD_single)."""
     out_loss, c = berhu_masked(outputs, depths, sparse)
     rmse = torch.sqrt(((outputs - depths) ** 2).detach().mean())  # diagnostic, trainer.py:722-723
-    lat = latent_loss(feats, feats_tar) if feats is not None else torch.zeros((), device=outputs.device)
+    lat = latent_loss(feats, feats_tar, guidance_grad) if feats is not None else torch.zeros((), device=outputs.device)
     smooth = (0.1 * depth_smoothness(outputs, rgb)).abs().mean()
     return {"loss": out_loss + lat + smooth, "output_loss": out_loss, "latent_loss": lat,
             "smooth_loss": smooth, "rmse_loss": rmse, "c": c}

@@ -1,0 +1,92 @@
+"""CPU: the engine's launch PLANS executed against a CPU emulation of the C ABI (tests/abi_emulator.py).
+
+The engine is a plan builder (descriptors -> library calls); the plan's correctness is independent of the GPU.
+These tests run it on raw pointers into CPU tensors, with every entry point emulated from the semantics documented
+in include/gdn_b200.h, and compare with the oracle.  They do NOT exercise the CUDA kernels (tests -m gpu do) and
+the product has no such path: gdn_pytorch_b200 refuses CPU tensors (tests/test_abi_cpu.py)."""
+import pytest
+import torch
+
+from tests.abi_emulator import emulated_abi, engine_forward, run_ops
+from tests.util import build_module, shapes_of, relerr
+
+H, W, B = 32, 64, 2
+
+
+def _module(name, seed, signed=False):
+    from oracle import synth
+    m = build_module(name, init_weights=False, height=H, width=W)
+    sd = synth.synth_state_dict(shapes_of(name), seed=seed)
+    if signed:
+        for k in sd:
+            if k.endswith(".weight") and sd[k].dim() == 1:
+                sd[k][::3] *= -1.0
+    m.load_state_dict(sd)
+    m.eval()
+    return m, sd
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("name,cin", [("AutoEncoder_2", 3), ("AutoEncoder_DtoD", 1), ("AutoEncoder", 3)])
+def test_eval_forward_plan_matches_oracle(name, cin):
+    from gdn_pytorch_b200.engine import Engine
+    from gdn_pytorch_b200.module_runtime import _params
+    from oracle import model as OM, synth
+    m, sd = _module(name, 0)
+    x = synth.synth_rgb(B, H, W, 0) if cin == 3 else synth.synth_depth(B, H, W, 0)
+    with emulated_abi() as emu:
+        g = m.gdn_graph()
+        eng = Engine(g, _params(m), B, H, W, train=False, want=g.outputs, device=torch.device("cpu"))
+        engine_forward(eng, x)
+        ref = OM.FORWARDS[name](sd, x, istrain=True)
+        for nm, r in zip(g.outputs, ref):
+            got = _nchw(eng.value(nm)).reshape(r.shape)
+            assert relerr(got, r) <= 1e-2, (nm, relerr(got, r))
+        assert emu.calls["gdn_conv2d"] == len(eng.units)
+
+
+def _l2rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_frozen_backward_plan_matches_autograd():
+    """Engine(train=False, backward=True, input_grad=True, grad_seeds=...): the opt-in guidance gradient
+     through the frozen DtoD encoder, against torch autograd through the oracle"""
+    from gdn_pytorch_b200.engine import Engine
+    from gdn_pytorch_b200.module_runtime import _params
+    from gdn_pytorch_b200.ops import LossKernels
+    from oracle import model as OM, losses as OL, synth
+    m, sd = _module("AutoEncoder_DtoD", 1, signed=True)
+    x, tar_in = synth.synth_depth(B, H, W, 3), synth.synth_depth(B, H, W, 4)
+    with torch.no_grad():
+        rt = OM.autoencoder_dtod(sd, tar_in, encoder_only=True)
+    xr = x.clone().requires_grad_(True)
+    lat = OL.latent_loss(OM.autoencoder_dtod(sd, xr, encoder_only=True), rt, with_grad=True)
+    (ref,) = torch.autograd.grad(lat, xr)
+    with emulated_abi():
+        g = m.gdn_graph()
+        names = g.encoder_outputs
+        eng = Engine(g, _params(m), B, H, W, train=False, backward=True, want=names, stop_after=names[-1],
+                     device=torch.device("cpu"), input_grad=True, grad_seeds=names)
+        kern = LossKernels.__new__(LossKernels)
+        kern.L = eng.L
+        ft_tar = [r.permute(0, 2, 3, 1).contiguous() for r in rt]
+        import gdn_pytorch_b200._lib as _l
+        orig = _l.stream_ptr
+        _l.stream_ptr = lambda: None
+        try:
+            for rep in range(2):            # seeds are rewritten every pass; nothing accumulates across passes
+                engine_forward(eng, x)
+                ft = [eng.value(n) for n in names]
+                kern.latent_grad(ft, ft_tar, [eng.dact[n] for n in names])
+                run_ops(eng.bwd)
+        finally:
+            _l.stream_ptr = orig
+        got = eng.dact["in"].reshape(B, 1, H, W)
+    assert torch.isfinite(got).all()
+    cos = (torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())).item()
+    assert cos >= 0.998, cos
+    assert _l2rel(got, ref) <= 5e-2, _l2rel(got, ref)

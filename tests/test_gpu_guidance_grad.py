@@ -1,0 +1,123 @@
+"""GPU (-m gpu): the opt-in guidance gradient.
+
+The published trainer wraps both frozen-DtoD passes in no_grad (/root/reference/src/trainer.py:699-703), so the
+default step treats the latent loss as a constant (tests/test_gpu_network.py::test_rtod_train_step_against_oracle).
+With ``guidance_grad=True`` the latent loss back-propagates through the frozen, eval-mode DtoD encoder into the
+RtoD output.  Oracle: torch autograd through the fp32 restatement of the same encoder (oracle/model.py, pinned on
+the reference's own outputs) -- i.e. what the reference computes once the no_grad is removed.
+
+Tolerance: gradients pass ~25 bf16 input-gradient convolutions (bf16 operands are mandated by the north star);
+L2-relative error <= 5e-2 (measured ~1e-2), cosine >= 0.998."""
+import pytest
+import torch
+
+from tests.test_gpu_network import _module, _inputs, B, H, W, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _l2rel(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _cos(a, b):
+    return (torch.dot(a.flatten(), b.flatten()) / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def _dtod_with_signed_gammas(seed=1):
+    """frozen DtoD net whose BatchNorm gammas have mixed signs (the ReLU mask must come from the unit's output, not
+    from the sign of scale*x)"""
+    m, sd = _module("AutoEncoder_DtoD", seed=seed)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k in sd:
+        if k.endswith(".weight") and sd[k].dim() == 1:
+            sd[k][::3] *= -1.0
+    m.load_state_dict(sd)
+    m.eval()
+    return m, sd
+
+
+def test_frozen_encoder_input_gradient_matches_autograd():
+    """Engine(train=False, backward=True, input_grad=True): d(sum_i coef_i * |ft_i - tar_i|^2 / 2) / d(input)"""
+    from gdn_pytorch_b200.engine import Engine
+    from gdn_pytorch_b200.module_runtime import _params
+    from gdn_pytorch_b200.ops import LossKernels
+    from oracle import model as OM, losses as OL
+    m, sd = _dtod_with_signed_gammas()
+    g = m.gdn_graph()
+    names = g.encoder_outputs
+    x, tar_in = _inputs(1, seed=3), _inputs(1, seed=4)
+    eng = Engine(g, _params(m), B, H, W, train=False, backward=True, want=names, stop_after=names[-1],
+                 device=torch.device(dev), input_grad=True, grad_seeds=names)
+    tar = Engine(g, _params(m), B, H, W, train=False, backward=False, want=names, stop_after=names[-1],
+                 device=torch.device(dev))
+    tar.forward(tar_in.to(dev))
+    ft_tar = [tar.value(n) for n in names]
+    kern = LossKernels(torch.device(dev))
+    for rep in range(2):      # twice: seeds are rewritten, nothing accumulates across calls
+        eng.forward(x.to(dev))
+        ft = [eng.value(n) for n in names]
+        kern.latent_grad(ft, ft_tar, [eng.dact[n] for n in names])
+        eng.run_backward()
+    got = eng.dact["in"].detach().cpu().reshape(B, 1, H, W)
+    xr = x.clone().requires_grad_(True)
+    with torch.no_grad():
+        rt = OM.autoencoder_dtod(sd, tar_in, encoder_only=True)
+    lat = OL.latent_loss(OM.autoencoder_dtod(sd, xr, encoder_only=True), rt, with_grad=True)
+    (ref,) = torch.autograd.grad(lat, xr)
+    assert torch.isfinite(got).all()
+    assert _cos(got, ref) >= 0.998, _cos(got, ref)
+    assert _l2rel(got, ref) <= 5e-2, _l2rel(got, ref)
+
+
+def test_rtod_step_with_guidance_gradient():
+    """RtoDTrainStep(guidance_grad=True): dL/d(pre-tanh) handed to the RtoD backward = (BerHu + smoothness + latent)
+    gradient of the oracle on the engine's own output; the default step's dpre has no latent part."""
+    from gdn_pytorch_b200.trainer import RtoDTrainStep
+    from oracle import model as OM, losses as OL, synth
+    rgb, dep = synth.synth_rgb(B, H, W, 0), synth.synth_depth(B, H, W, 0)
+    spa = synth.synth_sparse(dep, 0)
+    res = {}
+    for gg in (True, False):
+        rtod, _ = _module("AutoEncoder_2", seed=0)
+        dtod, sdd = _module("AutoEncoder_DtoD", seed=1)
+        dtod.eval()
+        rtod.train()
+        step = RtoDTrainStep(rtod, dtod, lr=2e-5, guidance_grad=gg)
+        step.use_graph = False
+        terms = step.step(rgb.to(dev), dep.to(dev), spa.to(dev))
+        out = step.eng.depth().detach().cpu()
+        dpre = step.eng.dpre.detach().cpu().reshape(B, 1, H, W)
+        o = out.clone().requires_grad_(True)
+        with torch.no_grad():
+            ft_tar = OM.autoencoder_dtod(sdd, dep, encoder_only=True)
+        ft = OM.autoencoder_dtod(sdd, o, encoder_only=True)
+        ref = OL.rtod_loss(o, dep, spa, rgb, ft, ft_tar, guidance_grad=gg)
+        (dout,) = torch.autograd.grad(ref["loss"], o)
+        ref_dpre = dout * (1 - out * out)
+        assert abs(float(terms["latent_loss"]) - float(ref["latent_loss"])) <= 5e-3 * abs(float(ref["latent_loss"]))
+        assert abs(float(terms["loss"]) - float(ref["loss"])) <= 5e-3 * abs(float(ref["loss"]))
+        assert _l2rel(dpre, ref_dpre) <= (5e-2 if gg else 1e-4), (gg, _l2rel(dpre, ref_dpre))
+        assert torch.isfinite(step.eng.flat_grad).all().item()
+        res[gg] = (dpre, ref_dpre)
+    # the guidance part itself (difference of the two runs' references is not available: outputs are identical only
+    # up to atomics noise) -- check it is a non-trivial share of the gradient and matches in direction
+    lat_part = res[True][0] - res[False][0]
+    lat_ref = res[True][1] - res[False][1]
+    assert lat_ref.norm() > 1e-3 * res[True][1].norm()
+    assert _cos(lat_part, lat_ref) >= 0.99, _cos(lat_part, lat_ref)
+
+
+def test_guidance_gradient_survives_graph_replay():
+    """the captured CUDA graph of the opt-in step replays: finite losses that change as the weights move"""
+    from gdn_pytorch_b200.trainer import RtoDTrainStep
+    from oracle import synth
+    rtod, _ = _module("AutoEncoder_2", seed=0)
+    dtod, _ = _module("AutoEncoder_DtoD", seed=1)
+    dtod.eval()
+    rtod.train()
+    rgb, dep = synth.synth_rgb(B, H, W, 0).to(dev), synth.synth_depth(B, H, W, 0).to(dev)
+    step = RtoDTrainStep(rtod, dtod, lr=1e-4, guidance_grad=True)
+    losses = [float(step.step(rgb, dep, None)["loss"]) for _ in range(5)]     # 2 eager + capture + 2 replays
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
+    assert len(set(losses)) > 1
