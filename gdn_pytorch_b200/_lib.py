@@ -52,6 +52,7 @@ def lib():
         L.gdn_last_error.restype = C.c_char_p
         L.gdn_version.restype = C.c_int
         L.gdn_sm_count.restype = C.c_int
+        L.gdn_resize_u8_workspace.restype = C.c_size_t
         _lib = L
     return _lib
 

@@ -21,6 +21,10 @@
  *   gdn_eigen_metrics     src/calculate_error.py:10-103
  *   gdn_adam_step         optim.Adam(lr, [0.9,0.999], eps=1e-8, weight_decay=5e-4): src/GDN_main.py:157,173
  *   gdn_pack_weights / gdn_unpack_wgrad   fp32 OIHW <-> bf16 [tap][Cout][Cin] operand layout (BN folding at eval)
+ *   gdn_act_backward_frozen / gdn_sqdiff_grad / gdn_tanh_chain_add   opt-in guidance gradient: autograd of the frozen
+ *                         DtoD encoder passes of src/trainer.py:699-703,726-733 with the no_grad removed
+ *   gdn_preprocess_u8     src/transform_list.py:84-113,161-203 (data-loader transforms)
+ *   gdn_bytescale / gdn_resize_u8   scipy.misc.imresize in src/depth_extract.py:23-58,86,138 (demo path)
  */
 #ifndef GDN_B200_H
 #define GDN_B200_H
@@ -208,6 +212,21 @@ int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int 
  * (gdn_pytorch_b200/data.py replays the reference's RNG calls). */
 int gdn_preprocess_u8(const uint8_t* src, float* dst, int n, int h, int w, int c, const int32_t* flip, const float* crop,
                       gdn_stream stream);
+
+/* ---- demo path: the image resizing of src/depth_extract.py:23-58,86,138 ------------------------
+ * scipy.misc.imresize(arr, size, 'bilinear') = bytescale + PIL BILINEAR resize of the 8-bit image, bit-exact.
+ * gdn_bytescale: dst[i] = uint8(clip((src[i] - min) * (255 / (max - min or 1)), 0, 255) + 0.5); src is float32 (or
+ *   uint8 storage of the float image when src_is_u8); f64_math = 0: float32 arithmetic (NumPy on the float32 input
+ *   image, :86), 1: double (the demo copies the depth map into a float64 array first, :135-138);
+ *   scratch8 = 8 bytes of device scratch.
+ * gdn_resize_u8: src uint8 [n][h][w][c] -> dst uint8 [n][oh][ow][c]; PIL's two-pass (horizontal, then vertical)
+ *   antialiased triangle filter with 22-bit fixed-point coefficients (Pillow src/libImaging/Resample.c).  The caller
+ *   owns the workspace (coefficient tables + the 8-bit intermediate): gdn_resize_u8_workspace() bytes. */
+int gdn_bytescale(const void* src, int src_is_u8, int64_t n, int f64_math, uint8_t* dst, void* scratch8,
+                  gdn_stream stream);
+size_t gdn_resize_u8_workspace(int n, int h, int w, int c, int oh, int ow);
+int gdn_resize_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int c, int oh, int ow, void* workspace,
+                  size_t ws_bytes, gdn_stream stream);
 
 /* ---- training loss, metrics, optimizer ------------------------------------------------------------------ */
 

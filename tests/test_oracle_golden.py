@@ -180,3 +180,45 @@ def test_transform_restatement_matches_reference_classes():
     random.seed(1)                                               # first draw 0.134 < 0.5 -> flips
     flipped = tl.RandomHorizontalFlip()([rgb.copy()])[0]
     assert np.array_equal(flipped.astype(np.uint8), OT.flip_scale_crop(rgb.astype(np.uint8), True, None))
+
+
+# ---------------------------------------------------------------------------------------- demo path: imresize
+def test_imresize_oracle_matches_pillow_golden():
+    """oracle/imresize.py::resize_u8 == PIL.Image.resize(BILINEAR), bit-exact, on the committed fixtures
+    (tests/golden/imresize.npz, written by oracle/gen_golden_imresize.py from Pillow itself)"""
+    from oracle import imresize as OI
+    from oracle.gen_golden_imresize import CASES, case_input, digest
+    gold = golden("imresize.npz")
+    for i, (seed, h, w, c, oh, ow) in enumerate(CASES):
+        got = OI.resize_u8(case_input(seed, h, w, c), (oh, ow))
+        assert np.array_equal(got[:24, :24], gold["case%d_corner" % i]), i
+        assert digest(got) == str(gold["case%d_sha256" % i]), i
+
+
+def test_imresize_oracle_matches_pillow_live():
+    """same, against the Pillow in this environment when it imports (other sizes than the fixtures)"""
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import imresize as OI
+    rng = np.random.RandomState(7)
+    for (h, w, c, oh, ow) in [(64, 96, 3, 23, 200), (31, 17, 1, 31, 40), (90, 120, 3, 128, 416), (16, 16, 1, 5, 3)]:
+        img = rng.randint(0, 256, (h, w, c)).astype(np.uint8)
+        img = img[:, :, 0] if c == 1 else img
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(OI.resize_u8(img, (oh, ow)), ref), (h, w, c, oh, ow)
+
+
+def test_bytescale_oracle_properties():
+    """scipy.misc.bytescale restatement (unpinned: SciPy >= 1.3 has no imresize): uint8 passes through, the extremes
+    map to 0 / 255, a constant image maps to 0, float64 and float32 evaluation agree except at .5 boundaries"""
+    from oracle import imresize as OI
+    rng = np.random.RandomState(3)
+    a = rng.randint(0, 256, (20, 30)).astype(np.uint8)
+    assert OI.bytescale(a) is a or np.array_equal(OI.bytescale(a), a)
+    f = np.tanh(rng.randn(40, 50)).astype(np.float32)
+    b = OI.bytescale(f)
+    assert b.dtype == np.uint8 and b.min() == 0 and b.max() == 255
+    assert OI.bytescale(np.full((4, 4), 3.5, np.float32)).max() == 0
+    full = np.arange(256, dtype=np.float32).reshape(16, 16)
+    assert np.array_equal(OI.bytescale(full), np.arange(256).reshape(16, 16))       # identity on a full-range image
+    d = np.abs(OI.bytescale(f.astype(np.float64)).astype(int) - b.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
