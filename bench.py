@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="train", choices=["train", "train_dtod", "infer", "infer_fullres"])
+    ap.add_argument("--workload", default="train", choices=["train", "train_guided", "train_dtod", "infer", "infer_fullres", "demo"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -238,15 +238,18 @@ def main():
     rank, world, dev = init_distributed_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
-    B = args.batch or (20 if args.workload.startswith("train") else 8)
+    B = args.batch or (20 if args.workload.startswith("train") else (1 if args.workload == "demo" else 8))
     h, w = (FULL_H, FULL_W) if args.workload == "infer_fullres" else (H, W)
     rgb_h, dep_h, spa_h = [t.pin_memory() for t in synth_batch(B, rank, h, w)]
     rgb, dep, spa = rgb_h.to(dev), dep_h.to(dev), spa_h.to(dev)
     rtod, dtod = build_models(dev, h, w)
     launches = [0]
 
-    if args.workload == "train":
-        stepper = RtoDTrainStep(rtod, dtod, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    if args.workload in ("train", "train_guided"):
+        # train_guided: the opt-in paper-faithful variant -- the latent loss back-propagates
+        # through the frozen DtoD encoder (its input-gradient convolutions are extra work: + 2 x 175.48 GFLOP/img)
+        guided = args.workload == "train_guided"
+        stepper = RtoDTrainStep(rtod, dtod, lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4, guidance_grad=guided)
 
         def step_dev():
             return stepper.step(rgb, dep, spa)
@@ -258,9 +261,12 @@ def main():
             return float(stepper.step(r, d, s)["loss"])   # D2H read of the loss
         h2d = (rgb_h.numel() + dep_h.numel() + spa_h.numel()) * 4
         d2h = 8
-        gflop_img = GFLOP_RTOD_TRAIN
+        gflop_img = GFLOP_RTOD_TRAIN + (175.48 if guided else 0.0)
         metric = "RtoD train imgs/s @128x416"
         workload = RTOD_TRAIN_WORKLOAD % B
+        if guided:
+            metric = "RtoD train (guidance gradient) imgs/s @128x416"
+            workload += " + latent-loss gradient through the frozen DtoD encoder (opt-in, SURVEY 8f row 3)"
     elif args.workload == "train_dtod":
         from gdn_pytorch_b200.trainer import DtoDTrainStep
         dtod.train()
@@ -279,6 +285,37 @@ def main():
         metric = "DtoD train imgs/s @128x416"
         workload = ("DtoD training step, batch %d per GPU, 128x416 (BASELINE configs[2]): AutoEncoder_DtoD fwd + BerHu/"
                     "Sobel loss + bwd + fused Adam" % B)
+    elif args.workload == "demo":
+        # the body of depth_extract.py's loop for one KITTI-sized frame at batch 1 --
+        # imresize -> normalise -> AutoEncoder (one CUDA graph) -> imresize back to the original size, 8-bit output
+        import contextlib, io
+        import numpy as np
+        from gdn_pytorch_b200 import AE_model_unet as M
+        from gdn_pytorch_b200.demo import DepthExtractor
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(0)
+            ae = M.AutoEncoder(height=H, width=W).to(dev).eval()
+        ex = DepthExtractor(ae)
+        frames_h = [torch.from_numpy(np.random.RandomState(rank * 7 + i).randint(0, 256, (375, 1242, 3)).astype(np.uint8))
+                    .pin_memory() for i in range(B)]
+        frames = [f.to(dev) for f in frames_h]
+        host_out = torch.empty((375, 1242), dtype=torch.uint8).pin_memory()
+
+        def step_dev():
+            for f in frames:
+                ex(f)
+
+        def step_e2e():
+            for f in frames_h:
+                host_out.copy_(ex(f.to(dev, non_blocking=True)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d = B * 375 * 1242 * 3
+        d2h = B * 375 * 1242
+        gflop_img = 683.35
+        metric = "demo imgs/s @375x1242 -> 128x416 -> 375x1242, batch 1"
+        workload = ("depth_extract.py loop body, %d frame(s) of 375x1242x3 uint8 per step, one at a time: imresize -> "
+                    "normalise -> AutoEncoder B=1 (CUDA graph) -> imresize back -> uint8 depth image" % B)
+        stepper = None
     else:
         from gdn_pytorch_b200.module_runtime import encoder_features
         rtod.eval()
@@ -376,9 +413,13 @@ def main():
                    "sample": "1 warm-up + %d timed RtoD training steps at batch 2 (fp32 torch CPU ops with all host "
                              "threads, oracle port of trainer.py:696-768)" % nrep}
         eng = getattr(locals().get("stepper", None), "eng", None)
-        if args.workload == "train":
+        if args.workload in ("train", "train_guided"):
             per_step = (eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) +
-                        sum(e.launches_fwd for e in stepper.deng if e is not None) + 2 + 4 + 1)
+                        sum(e.launches_fwd + getattr(e, "launches_bwd", 0) for e in stepper.deng if e is not None) +
+                        2 + 4 + 1 + (5 if args.workload == "train_guided" else 0))
+        elif args.workload == "demo":
+            # per frame: 3 bytescale + <= 4 resize (in) + normalise + network + 3 bytescale + <= 4 resize (out)
+            per_step = B * (ex.eng.launches_fwd + 15)
         elif args.workload == "train_dtod":
             per_step = eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) + 2 + 1
         else:
