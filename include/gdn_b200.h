@@ -86,11 +86,11 @@ typedef struct {
 
 int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream);
 
-/* Weight gradient: dw[tap][co][ci] (fp32, += ) = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride + r + off_y, ox*stride + s + off_x, ci] */
+/* Weight gradient: dw[tap][ci][co] (fp32, += ) = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride + r + off_y, ox*stride + s + off_x, ci] */
 typedef struct {
   gdn_act x0, x1;            /* forward input(s) of the convolution (virtual concat like gdn_conv_desc) */
   gdn_act dy;                /* gradient of the conv output, interior = out_h x out_w, c = cout_pad */
-  float* dw;                 /* fp32 [kh*kw][cout_pad][cin_total], accumulated into (caller zeroes) */
+  float* dw;                 /* fp32 [kh*kw][cin_total][cout_pad] (co fastest), accumulated into (caller zeroes) */
   int32_t kh, kw, stride, off_y, off_x, out_h, out_w, cout_pad;
 } gdn_wgrad_desc;
 

@@ -6,9 +6,10 @@ reflection folds ...) does not depend on the GPU, so the CPU suite runs the plan
 implements the documented semantics of each entry point with torch CPU ops on the SAME descriptors (raw pointers
 into CPU tensors).  bf16 operand rounding is reproduced (operands are read from bf16 buffers), accumulation is fp32.
 
-Covered: gdn_bn_fold, gdn_pack_weights, gdn_im2col, gdn_conv2d, gdn_act_forward, gdn_act_backward_frozen,
-gdn_fold_grad, gdn_sqdiff_sum, gdn_sqdiff_grad, gdn_tanh_chain_add.  The training-only entry points (batch
-statistics, weight gradients, Adam) raise.
+Covered: gdn_bn_fold, gdn_bn_finalize, gdn_pack_weights, gdn_unpack_wgrad, gdn_im2col, gdn_conv2d, gdn_conv2d_wgrad,
+gdn_act_forward, gdn_bn_bwd_reduce, gdn_act_backward, gdn_act_backward_frozen, gdn_fold_grad, gdn_sqdiff_sum,
+gdn_sqdiff_grad, gdn_tanh_chain_add.  Loss, metrics, Adam and the image kernels are not emulated (they have direct
+GPU-vs-oracle tests).
 
 Use:  with emulated_abi():  eng = Engine(..., device=torch.device("cpu")); run_ops(eng.fwd) ...
 """
@@ -231,23 +232,129 @@ class EmulatedLib:
         sc = 2 if (f.up or f.dilate) else 1
         Hq, Wq = f.h * sc + 2 * f.pad, f.w * sc + 2 * f.pad
         dpad = _t(f.dpad, (f.n, Hq, Wq, f.ctot), torch.float32)[..., f.c_off:f.c_off + f.c].permute(0, 3, 1, 2)
-        x = torch.zeros((f.n, f.c, f.h, f.w), requires_grad=True)
-        z = x
-        if f.up:
-            z = F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=(f.up == 2))
-        elif f.dilate:
-            zz = torch.zeros((f.n, f.c, 2 * f.h, 2 * f.w))
-            zz[:, :, ::2, ::2] = z
-            z = zz
-        if f.pad:
-            z = F.pad(z, (f.pad,) * 4, mode="reflect" if f.reflect else "constant")
-        (gx,) = torch.autograd.grad(z, x, dpad.contiguous())
+        with torch.enable_grad():             # the adjoint of the input transform, by autograd of the transform itself
+            x = torch.zeros((f.n, f.c, f.h, f.w), requires_grad=True)
+            z = x
+            if f.up:
+                z = F.interpolate(z, scale_factor=2, mode="bilinear", align_corners=(f.up == 2))
+            elif f.dilate:
+                zz = torch.zeros((f.n, f.c, 2 * f.h, 2 * f.w))
+                zz[:, :, ::2, ::2] = z
+                z = zz
+            if f.pad:
+                z = F.pad(z, (f.pad,) * 4, mode="reflect" if f.reflect else "constant")
+            (gx,) = torch.autograd.grad(z, x, dpad.contiguous())
         out = _t(f.dact, (f.n, f.h, f.w, f.c), torch.float32)
         gx = gx.permute(0, 2, 3, 1)
         if f.accumulate:
             out.add_(gx)
         else:
             out.copy_(gx)
+        return 0
+
+    # ---- training mode: batch statistics, BatchNorm backward, weight gradients
+    def _e_bn_finalize(self, sum_, sqsum, count, gamma, beta, eps, momentum, rmean, rvar, scale, shift, mean, rstd, c, s):
+        count, eps, momentum = (v.value if hasattr(v, "value") else v for v in (count, eps, momentum))
+        m = _t(sum_, (c,), torch.float64) / count
+        var = _t(sqsum, (c,), torch.float64) / count - m * m
+        rs = 1.0 / torch.sqrt(var + eps)
+        g, b = _t(gamma, (c,), torch.float32).double(), _t(beta, (c,), torch.float32).double()
+        _t(scale, (c,), torch.float32).copy_((g * rs).float())
+        _t(shift, (c,), torch.float32).copy_((b - m * g * rs).float())
+        _t(mean, (c,), torch.float32).copy_(m.float())
+        _t(rstd, (c,), torch.float32).copy_(rs.float())
+        if _addr(rmean):
+            rm, rv = _t(rmean, (c,), torch.float32), _t(rvar, (c,), torch.float32)
+            rm.mul_(1 - momentum).add_((momentum * m).float())
+            rv.mul_(1 - momentum).add_((momentum * var * count / (count - 1)).float())
+        return 0
+
+    def _bn_bwd_terms(self, b):
+        shp = (b.n, b.h, b.w, b.c)
+        g = _t(b.dact, shp, torch.float32).clone()
+        raw = _t(b.raw, shp, torch.float16 if b.raw_is_half else torch.bfloat16).float()
+        sc, sh = _t(b.scale, (b.c,), torch.float32), _t(b.shift, (b.c,), torch.float32)
+        if b.relu:
+            g = g * ((raw * sc + sh) > 0)
+        xhat = (raw - _t(b.mean, (b.c,), torch.float32)) * _t(b.rstd, (b.c,), torch.float32)
+        return g, xhat, sc
+
+    def _e_bn_bwd_reduce(self, bref, s):
+        b = _obj(bref)
+        g, xhat, _ = self._bn_bwd_terms(b)
+        _t(b.sum_g, (b.c,), torch.float64).add_(g.double().sum((0, 1, 2)))
+        _t(b.sum_gx, (b.c,), torch.float64).add_((g * xhat).double().sum((0, 1, 2)))
+        return 0
+
+    def _e_act_backward(self, bref, s):
+        b = _obj(bref)
+        g, xhat, sc = self._bn_bwd_terms(b)
+        npix = float(b.n * b.h * b.w)
+        sg, sgx = _t(b.sum_g, (b.c,), torch.float64), _t(b.sum_gx, (b.c,), torch.float64)
+        dy = sc * (g - (sg / npix).float() - xhat * (sgx / npix).float())
+        assert not b.dilate
+        _t(b.dy, (b.n, b.h, b.w, b.c), torch.bfloat16).copy_(dy.to(torch.bfloat16))
+        if b.dgamma:
+            _t(b.dgamma, (b.c,), torch.float32).add_(sgx.float())
+            _t(b.dbeta, (b.c,), torch.float32).add_(sg.float())
+        return 0
+
+    def _e_conv2d_wgrad(self, wref, s):
+        w = _obj(wref)
+
+        def phys(a):
+            return _t(a.ptr, (a.n, a.h + 2 * a.pad, a.w + 2 * a.pad, a.c), torch.bfloat16).float()
+        X, p = phys(w.x0), w.x0.pad
+        if w.x1.ptr:
+            X = torch.cat((X, phys(w.x1)), -1)
+        n, Hp, Wp, cin = X.shape
+        dy = _t(w.dy.ptr, (n, w.out_h, w.out_w, w.cout_pad), torch.bfloat16).float()
+        assert (w.dy.h, w.dy.w, w.dy.c, w.dy.pad) == (w.out_h, w.out_w, w.cout_pad, 0)
+        st = w.stride
+        ylo, xlo = w.off_y + p, w.off_x + p
+        yhi, xhi = (w.out_h - 1) * st + w.kh - 1 + ylo, (w.out_w - 1) * st + w.kw - 1 + xlo
+        pt, pl = max(0, -ylo), max(0, -xlo)
+        pb, pr = max(0, yhi - (Hp - 1)), max(0, xhi - (Wp - 1))
+        Xn = F.pad(X.permute(0, 3, 1, 2), (pl, pr, pt, pb)).permute(0, 2, 3, 1)
+        dw = _t(w.dw, (w.kh * w.kw, cin, w.cout_pad), torch.float32)
+        for r in range(w.kh):
+            for q in range(w.kw):
+                y0, x0 = ylo + pt + r, xlo + pl + q
+                xs = Xn[:, y0: y0 + (w.out_h - 1) * st + 1: st, x0: x0 + (w.out_w - 1) * st + 1: st]
+                dw[r * w.kw + q] += torch.einsum("nyxi,nyxo->io", xs, dy)
+        return 0
+
+    def _e_unpack_wgrad(self, pd, dw, grad, accumulate, s):
+        k = _obj(pd)
+        T = 1 if k.col_c else k.kh * k.kw
+        src = _t(dw, (T, k.b_pad, k.a_pad), torch.float32)
+        base = _addr(grad)
+        ai = torch.arange(k.a)
+
+        def scatter(idx, vals):
+            lo, hi = int(idx.min()), int(idx.max())
+            flat = _t(base + 4 * lo, (hi - lo + 1,), torch.float32)
+            ii = (idx - lo).reshape(-1)
+            if accumulate:
+                flat.index_add_(0, ii, vals.reshape(-1))
+            else:
+                flat[ii] = vals.reshape(-1)
+        if k.col_c:
+            for tt in range(k.kh * k.kw):
+                r, s2 = divmod(tt, k.kw)
+                if k.flip:
+                    r, s2 = k.kh - 1 - r, k.kw - 1 - s2
+                for c in range(k.col_c):
+                    scatter(ai * k.stride_a + c * k.stride_b + r * k.stride_r + s2 * k.stride_s,
+                            src[0, tt * k.col_c + c, :k.a])
+        else:
+            bi = torch.arange(k.b)
+            for t in range(T):
+                r, s2 = divmod(t, k.kw)
+                if k.flip:
+                    r, s2 = k.kh - 1 - r, k.kw - 1 - s2
+                idx = ai[:, None] * k.stride_a + bi[None, :] * k.stride_b + r * k.stride_r + s2 * k.stride_s
+                scatter(idx, src[t, :k.b, :k.a].t())
         return 0
 
     # ---- guidance-loss helpers
@@ -277,9 +384,10 @@ def emulated_abi():
     (they are GPU-side optimisations of the same calls)"""
     from gdn_pytorch_b200 import _lib
     saved = _lib._lib
-    env = {k: os.environ.get(k) for k in ("GDN_AUTOTUNE", "GDN_PACK_TABLE")}
+    env = {k: os.environ.get(k) for k in ("GDN_AUTOTUNE", "GDN_PACK_TABLE", "GDN_SIDE")}
     os.environ["GDN_AUTOTUNE"] = "0"
     os.environ["GDN_PACK_TABLE"] = "0"
+    os.environ["GDN_SIDE"] = "0"              # no CUDA side streams: the plan runs in list order
     emu = EmulatedLib()
     _lib._lib = emu
     try:

@@ -90,3 +90,51 @@ def test_frozen_backward_plan_matches_autograd():
     cos = (torch.dot(got.flatten(), ref.flatten()) / (got.norm() * ref.norm())).item()
     assert cos >= 0.998, cos
     assert _l2rel(got, ref) <= 5e-2, _l2rel(got, ref)
+
+
+@pytest.mark.parametrize("gname", ["mini_rtod", "mini_dtod", "mini_deep512"])
+def test_training_plan_forward_backward_matches_autograd(gname):
+    """The TRAINING plan (batch-statistics BatchNorm, BN backward, sub-pixel stride-2 dgrad, upsample / reflection /
+    dilation folds, virtual concat, im2col'd thin layers and heads, weight-gradient unpack) on shallow graphs that
+    contain every unit type -- same comparison as tests/test_gpu_network.py::test_backward_on_shallow_graphs, with the
+    emulated ABI instead of the GPU: fp64 autograd with the engine's ReLU masks imposed."""
+    from gdn_pytorch_b200.engine import Engine
+    from oracle import synth
+    from oracle.graph_interp import run_graph
+    from tests import minigraphs
+    g = getattr(minigraphs, gname)()
+    sd = minigraphs.synth_params(g, 0)
+    for k, v in sd.items():
+        if not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    x = synth.synth_rgb(B, H, W, 1) if g.cin == 3 else synth.synth_depth(B, H, W, 1)
+    R = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(5)) - 0.5
+    names = [u.out for u in g.units]
+    with emulated_abi():
+        eng = Engine(g, sd, B, H, W, train=True, backward=True, want=names, device=torch.device("cpu"))
+        with torch.no_grad():
+            engine_forward(eng, x)
+            masks = {u.out: (eng.value_nchw(u.out) > 0) for u in g.units if u.relu and not u.resid}
+            out = eng.depth()
+            eng.flat_grad.zero_()
+            eng.dpre.copy_((R * (1 - out * out)).view(B, H, W))
+            run_ops(eng.bwd)
+    sd64 = {k: v.detach().double().requires_grad_(v.requires_grad) for k, v in sd.items()}
+    T = run_graph(g, sd64, x.double(), train=True, relu_masks=masks)
+    for t in T.values():
+        if t.requires_grad:
+            t.retain_grad()
+    (T["out"] * R.double()).sum().backward()
+    for n in names:
+        assert relerr(eng.value_nchw(n), T[n].float()) <= 8e-2, n
+    for u in g.units:
+        if u.out != "out" and T[u.out].grad is not None:
+            a, b = eng.dact[u.out].permute(0, 3, 1, 2), T[u.out].grad.float()
+            assert _l2rel(a, b) <= 3e-2, u.out
+    checked = 0
+    for k, v in sd64.items():
+        if v.grad is None or v.grad.abs().max().item() < 1e-9:
+            continue
+        assert _l2rel(eng.grad[k], v.grad.float()) <= 3e-2, k
+        checked += 1
+    assert checked >= 2 * len(g.units) - 2
