@@ -160,7 +160,7 @@ def cpu_step_fn(B):
         opt.zero_grad()
         terms["loss"].backward()
         opt.step()
-        return float(terms["loss"])
+        return float(terms["loss"].detach())
     return step
 
 
