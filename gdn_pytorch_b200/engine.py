@@ -112,6 +112,7 @@ class Engine:
                 self._build_backward()
             else:
                 self._build_backward_frozen()
+        self._resolve_first_use()
         if os.environ.get("GDN_PACK_TABLE", "1") != "0":
             self.pack_ops = self._batch_packs(self.pack_ops)
             if backward:
@@ -252,7 +253,9 @@ class Engine:
                 others.append(op)
                 continue
             pd, wptr, sptr, optr, what = job
-            grp = groups.setdefault(pd.kh * pd.kw, {"blobs": [], "cta0": 0})
+            grp = groups.setdefault(pd.kh * pd.kw, {"blobs": [], "cta0": 0, "first_use": None})
+            fu = getattr(op, "first_use", 0)
+            grp["first_use"] = fu if grp["first_use"] is None else min(grp["first_use"], fu)
             buf = C.create_string_buffer(jsz)
             n = C.c_int(0)
             rc = L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(wptr), C.c_void_p(sptr), C.c_void_p(optr), grp["cta0"], buf,
@@ -275,6 +278,7 @@ class Engine:
                 if rc:
                     _lib.check(rc, "pack_weights_table")
             run.label = "pack-table"
+            run.first_use = grp["first_use"] or 0
             runs.append(run)
         return others + runs + left
 
@@ -294,6 +298,17 @@ class Engine:
         self.cu = {}
         self.launches_fwd = 0
         P = self.P
+        if self.train:
+            # per-channel sum / sum-of-squares accumulators of EVERY BatchNorm of the network in one fp64 buffer,
+            # cleared by one launch at the head of the forward plan (instead of one tiny fill per layer on the
+            # critical chain)
+            self.stat_all = torch.zeros(sum(2 * u.cout for u in self.units if u.bn is not None) + 2, dtype=torch.float64,
+                                        device=dev)
+            zero_stats = lambda s: self.stat_all.zero_()
+            zero_stats.label = "misc"
+            self.fwd.append(zero_stats)
+            self.launches_fwd += 1
+            stat_off = 0
         if not self.thin_in:
             c_in, h_in, w_in = self.shape["in"]
             self.fwd.append(lambda s: self.f32["in"].copy_(self._x.permute(0, 2, 3, 1)))
@@ -344,10 +359,12 @@ class Engine:
                                        C.c_void_p(cu.fold_bias.data_ptr()), c, s)
                     if rc:
                         _lib.check(rc, "bn_fold")
+                fold.cu = cu
                 self.pack_ops.append(fold)
                 self.pack_ops.append(self._pack_call(pd, wt, cu.fold_scale, cu.wf, "pack " + u.conv))
             else:
                 self.pack_ops.append(self._pack_call(pd, wt, None, cu.wf, "pack " + u.conv))
+            self.pack_ops[-1].cu = cu
 
             # ---------------- input operand(s)
             d = ConvDesc()
@@ -388,7 +405,8 @@ class Engine:
             if self.train and u.bn is not None:
                 # raw conv output + statistics, then BatchNorm apply into every variant the consumers need
                 cu.raw = torch.empty((N, ho, wo, u.cout), dtype=torch.float16, device=dev)
-                cu.stat = torch.zeros((2, u.cout), dtype=torch.float64, device=dev)
+                cu.stat = self.stat_all[stat_off:stat_off + 2 * u.cout].view(2, u.cout)
+                stat_off += 2 * u.cout
                 cu.scale = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.shift = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.mean = torch.empty(u.cout, dtype=torch.float32, device=dev)
@@ -397,7 +415,7 @@ class Engine:
                 d.out16_is_half = 1
                 d.stat_sum = cu.stat[0].data_ptr()
                 d.stat_sqsum = cu.stat[1].data_ptr()
-                self.fwd.append(lambda s, cu=cu: cu.stat.zero_())
+                cu.fwd_conv_idx = len(self.fwd)
                 self.fwd.append(self._call(L.gdn_conv2d, d, "conv " + u.conv))
                 g_, b_ = P[u.bn + ".weight"], P[u.bn + ".bias"]
                 rm, rv = P[u.bn + ".running_mean"], P[u.bn + ".running_var"]
@@ -467,6 +485,7 @@ class Engine:
                     v = direct[0]
                     d.out_bf16 = self._act_struct(u.out, v)
                     d.out_reflect = v[2]
+                cu.fwd_conv_idx = len(self.fwd)
                 self.fwd.append(self._call(L.gdn_conv2d, d, "conv " + u.conv))
                 self.launches_fwd += 1
                 for v in direct[1:] + derived:
@@ -480,6 +499,12 @@ class Engine:
                 if (direct[1:] or derived) and not self.need_f32[u.out]:
                     raise AssertionError("variant derivation needs the fp32 copy of " + u.out)
 
+    def _resolve_first_use(self):
+        """index of the forward op that first reads each weight pack (for packs issued on the side stream)"""
+        for op in self.pack_ops:
+            cu = getattr(op, "cu", None)
+            op.first_use = getattr(cu, "fwd_conv_idx", 0) if cu is not None else 0
+
     def _thin_input(self, name):
         if name == "in":
             return self._x
@@ -488,8 +513,28 @@ class Engine:
     # ------------------------------------------------------------------ running
     def refresh_weights(self, stream=None):
         s = stream or _lib.stream_ptr()
-        for op in self.pack_ops:
-            op(s)
+        side = self.side_stream
+        self._fwd_wait = None
+        if (side is not None and self.train and getattr(self, "async_fwd_pack", False)
+                and os.environ.get("GDN_ASYNC_FWD_PACK", "1") != "0"):
+            # fused training steps: the forward packs run on the side stream in order of first use, the forward
+            # plan waits for each pack just before the first convolution that reads it -- the big 3x3 / 512-channel
+            # tables (needed ~5 ms into the forward pass) are re-packed UNDER the first layers instead of in front
+            # of them (the re-pack was ~0.75 ms at the head of the step's critical chain)
+            main = torch.cuda.current_stream(self.dev)
+            side.wait_stream(main)
+            waits = {}
+            with torch.cuda.stream(side):
+                sp = C.c_void_p(side.cuda_stream)
+                for op in sorted(self.pack_ops, key=lambda o: getattr(o, "first_use", 0)):
+                    op(sp)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    waits[getattr(op, "first_use", 0)] = ev     # same stream: a later event covers the earlier packs
+            self._fwd_wait = waits
+        else:
+            for op in self.pack_ops:
+                op(s)
         if self.do_bwd:
             side = self.side_stream
             if side is not None and getattr(self, "async_bwd_pack", False):
@@ -529,12 +574,26 @@ class Engine:
             self.refresh_weights(s)
             self._wversion = ver
         tl = getattr(self, "timeline", None)
+        waits, self._fwd_wait = getattr(self, "_fwd_wait", None), None
+        if waits:
+            main = torch.cuda.current_stream(self.dev)
+            pending = sorted(waits.items())
+
+            def gate(i):                    # packs issued on the side stream: wait right before their first reader
+                while pending and pending[0][0] <= i:
+                    main.wait_event(pending.pop(0)[1])
+        else:
+            gate = None
         if tl is None:
-            for op in self.fwd:
+            for i, op in enumerate(self.fwd):
+                if gate is not None:
+                    gate(i)
                 op(s)
         else:                               # development aid (tools/timeline.py): completion event after every op
             cur = torch.cuda.current_stream(self.dev)
-            for op in self.fwd:
+            for i, op in enumerate(self.fwd):
+                if gate is not None:
+                    gate(i)
                 op(s)
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(cur)
@@ -589,7 +648,15 @@ class Engine:
             maxdw = max(maxdw, (1 if cu.thin else cu.k * cu.k) * (cu.kpad if cu.thin else u.cin) * max(cu.cout_pad, 64))
         maxdw = max(maxdw, 128 * 64)
         self.dw_scratch = torch.zeros(maxdw, dtype=torch.float32, device=dev)
-        self.bn_sums = torch.zeros((2, 512), dtype=torch.float64, device=dev)
+        # sum(g) / sum(g * xhat) accumulators of every BatchNorm-backward reduction, cleared by ONE launch at the head
+        # of the backward plan
+        n_bn = sum(1 for u in self.units if u.bn is not None)
+        self.bn_sums_all = torch.zeros((max(n_bn, 1), 2, 512), dtype=torch.float64, device=dev)
+        zero_sums = lambda s: self.bn_sums_all.zero_()
+        zero_sums.label = "misc"
+        self.bwd.append(zero_sums)
+        self.launches_bwd += 1
+        bn_i = 0
 
         order = []  # static accumulation bookkeeping: which tensors already hold a gradient at each point
         have = set()
@@ -636,12 +703,12 @@ class Engine:
             b.relu = int(u.relu)
             b.raw_is_half = 1
             b.n, b.h, b.w, b.c = N, ho, wo, u.cout
-            b.sum_g, b.sum_gx = self.bn_sums[0].data_ptr(), self.bn_sums[1].data_ptr()
+            b.sum_g, b.sum_gx = self.bn_sums_all[bn_i, 0].data_ptr(), self.bn_sums_all[bn_i, 1].data_ptr()
+            bn_i += 1
             b.dy = cu.dy.data_ptr()
             b.dilate = 0
             b.dgamma = self.grad[u.bn + ".weight"].data_ptr()
             b.dbeta = self.grad[u.bn + ".bias"].data_ptr()
-            self.bwd.append(lambda s: self.bn_sums.zero_())
             self.bwd.append(self._call(L.gdn_bn_bwd_reduce, b, "bn_bwd_reduce " + u.conv))
             self.bwd.append(self._call(L.gdn_act_backward, b, "act_backward " + u.conv))
             self.grad_ready_op[u.bn + ".weight"] = self.grad_ready_op[u.bn + ".bias"] = len(self.bwd) - 1

@@ -136,6 +136,7 @@ class _StepBase:
         self.eng = get_engine(self.model, self.graph, x, train=True, backward=True, want=())
         eng = self.eng
         eng.async_bwd_pack = True
+        eng.async_fwd_pack = True
         named = list(self.model.named_parameters())
         # the engine's flat gradient uses the same slot layout as flatten_parameters()
         assert eng.flat_grad.numel() == self.flat_params.numel(), (eng.flat_grad.numel(), self.flat_params.numel())
