@@ -84,10 +84,19 @@ class ClockSampler(threading.Thread):
 
 
 def synth_batch(B, seed, h=H, w=W):
-    from oracle import synth   # input generators only (shared with the tests); nothing of the oracle is timed here
-    rgb = synth.synth_rgb(B, h, w, seed)
-    dep = synth.synth_depth(B, h, w, seed)
-    spa = synth.synth_sparse(dep, seed)
+    """synthetic KITTI-shaped inputs (SURVEY.md 8d): rgb U[-1,1]; dense depth = vertical ramp + smooth blobs in [-1,1];
+    sparse = dense with 70 % of the pixels set to exactly -1.0 (the `sparse > -1` validity test of trainer.py:706).
+    Same generators and seeds as oracle/synth.py, restated here so that the product arm never imports oracle/."""
+    g = torch.Generator().manual_seed(seed + 11)
+    rgb = torch.rand((B, 3, h, w), generator=g) * 2 - 1
+    g = torch.Generator().manual_seed(seed + 23)
+    ys = torch.linspace(1.0, -1.0, h).view(1, 1, h, 1).expand(B, 1, h, w)
+    low = torch.rand((B, 1, max(h // 8, 1), max(w // 8, 1)), generator=g) * 2 - 1
+    blobs = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)
+    dep = (0.6 * ys + 0.5 * blobs).clamp(-1, 1).contiguous()
+    g = torch.Generator().manual_seed(seed + 37)
+    m = torch.rand(dep.shape, generator=g) < 0.3
+    spa = torch.where(m, dep, torch.full_like(dep, -1.0))
     return rgb, dep, spa
 
 

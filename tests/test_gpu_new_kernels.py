@@ -1,0 +1,138 @@
+"""GPU (-m gpu): the small kernels behind the guidance gradient, one by one against torch, and the CPU emulation of
+the ABI (tests/abi_emulator.py) against the real kernels on whole engine plans -- the emulator is what the CPU suite
+trusts for plan checks, so it is pinned here on the hardware it stands in for."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+@pytest.mark.parametrize("relu,use_f32,scaled", [(1, True, True), (1, False, True), (0, True, True), (1, True, False)])
+def test_act_backward_frozen(relu, use_f32, scaled):
+    from gdn_pytorch_b200 import _lib
+    from gdn_pytorch_b200.engine import FrozenBwdDesc
+    g = torch.Generator().manual_seed(3)
+    N, H, W, Cc = 3, 10, 14, 128
+    dact = (torch.randn((N, H, W, Cc), generator=g) * 1e-4).to(dev)
+    y = torch.relu(torch.randn((N, H, W, Cc), generator=g)).to(dev)
+    yb = y.to(torch.bfloat16)
+    scale = (torch.randn(Cc, generator=g)).to(dev)          # mixed signs on purpose
+    dy = torch.full((N, H, W, Cc), float("nan"), device=dev, dtype=torch.bfloat16)
+    d = FrozenBwdDesc()
+    d.dact = dact.data_ptr()
+    if relu:
+        if use_f32:
+            d.y_f32 = y.data_ptr()
+        else:
+            d.y_bf16 = yb.data_ptr()
+    d.scale = scale.data_ptr() if scaled else None
+    d.relu, d.n, d.h, d.w, d.c = relu, N, H, W, Cc
+    d.dy = dy.data_ptr()
+    _lib.check(_lib.lib().gdn_act_backward_frozen(C.byref(d), _lib.stream_ptr()), "frozen")
+    ref = dact.clone()
+    if relu:
+        ref = ref * ((y if use_f32 else yb.float()) > 0)
+    if scaled:
+        ref = ref * scale
+    assert torch.equal(dy, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("c,pad,reflect,acc", [(1, 4, 1, 0), (1, 4, 1, 1), (3, 2, 1, 0), (1, 3, 0, 0), (2, 0, 0, 1)])
+def test_fold_grad_thin_channels(c, pad, reflect, acc):
+    """adjoint of reflection / zero padding for 1..3-channel tensors (the input gradient of a first layer)"""
+    from gdn_pytorch_b200 import _lib
+    from gdn_pytorch_b200.engine import FoldDesc
+    g = torch.Generator().manual_seed(c + pad)
+    N, H, W = 2, 12, 20
+    dpad = torch.randn((N, H + 2 * pad, W + 2 * pad, c), generator=g).to(dev)
+    base = torch.randn((N, H, W, c), generator=g).to(dev)
+    out = base.clone()
+    f = FoldDesc()
+    f.dpad, f.ctot, f.c_off = dpad.data_ptr(), c, 0
+    f.n, f.h, f.w, f.c = N, H, W, c
+    f.pad, f.reflect, f.up, f.dilate = pad, reflect, 0, 0
+    f.dact, f.accumulate = out.data_ptr(), acc
+    _lib.check(_lib.lib().gdn_fold_grad(C.byref(f), _lib.stream_ptr()), "fold")
+    x = torch.zeros((N, c, H, W), device=dev, dtype=torch.float64, requires_grad=True)
+    z = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant") if pad else x
+    (gx,) = torch.autograd.grad(z, x, dpad.double().permute(0, 3, 1, 2))
+    ref = gx.permute(0, 2, 3, 1) + (base.double() if acc else 0)
+    assert torch.allclose(out.double(), ref, rtol=1e-6, atol=1e-6)
+
+
+def test_sqdiff_grad_and_tanh_chain_add():
+    from gdn_pytorch_b200.ops import LossKernels
+    g = torch.Generator().manual_seed(9)
+    k = LossKernels(torch.device(dev))
+    feats = [torch.randn((2, 8, 12, c), generator=g).to(dev) for c in (64, 128, 512, 512)]
+    tars = [torch.randn(f.shape, generator=g).to(dev) for f in feats]
+    grads = [torch.full_like(f, float("nan")) for f in feats]
+    k.latent_grad(feats, tars, grads)
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    lat = 1.5 * sum(w * F.mse_loss(a, b) for w, a, b in zip(k.LATENT_W, fr, tars)) / 4
+    ref = torch.autograd.grad(lat, fr)
+    for a, b in zip(grads, ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-12)
+    out = torch.tanh(torch.randn((2, 1, 16, 24), generator=g)).to(dev)
+    dout = torch.randn(out.shape, generator=g).to(dev)
+    dpre = torch.randn(out.shape, generator=g).to(dev)
+    want = dpre + 0.5 * dout * (1 - out * out)
+    k.tanh_chain_add(dout, out, dpre, scale=0.5)
+    assert torch.allclose(dpre, want, rtol=1e-6, atol=1e-7)
+
+
+def _l2(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("gname,train", [("mini_rtod", False), ("mini_dtod", False), ("mini_deep512", False),
+                                          ("mini_rtod", True), ("mini_dtod", True)])
+def test_abi_emulator_agrees_with_the_kernels(gname, train):
+    """same plan, same inputs: real kernels on the B200 vs tests/abi_emulator.py on the host.  Both sides round the
+    operands to bf16 identically; differences are fp32 accumulation order (and, in training, the few ReLU decisions
+    that order flips)."""
+    from gdn_pytorch_b200.engine import Engine
+    from oracle import synth
+    from tests import minigraphs
+    from tests.abi_emulator import emulated_abi, engine_forward, run_ops
+    B, H, W = 2, 32, 64
+    g = getattr(minigraphs, gname)()
+    sd = minigraphs.synth_params(g, 0)
+    x = synth.synth_rgb(B, H, W, 1) if g.cin == 3 else synth.synth_depth(B, H, W, 1)
+    R = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(5)) - 0.5
+    names = [u.out for u in g.units]
+
+    def params(device):
+        p = {k: v.clone().to(device) for k, v in sd.items()}
+        for k, v in p.items():
+            if train and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+        return p
+    eng = Engine(g, params(dev), B, H, W, train=train, backward=train, want=names)
+    with torch.no_grad():
+        eng.forward(x.to(dev))
+        if train:
+            out = eng.depth()
+            eng.flat_grad.zero_()
+            eng.backward((R.to(dev) * (1 - out * out)).view(B, H, W))
+    torch.cuda.synchronize()
+    with emulated_abi():
+        emu = Engine(g, params("cpu"), B, H, W, train=train, backward=train, want=names, device=torch.device("cpu"))
+        with torch.no_grad():
+            engine_forward(emu, x)
+            if train:
+                out = emu.depth()
+                emu.flat_grad.zero_()
+                emu.dpre.copy_((R * (1 - out * out)).view(B, H, W))
+                run_ops(emu.bwd)
+    tol = 3e-2 if train else 2e-3
+    for n in names:
+        assert _l2(eng.value(n).cpu(), emu.value(n)) <= tol, n
+    if train:
+        for k in emu.grad:
+            if emu.grad[k].abs().max().item() > 1e-9:
+                assert _l2(eng.grad[k].cpu(), emu.grad[k]) <= 5e-2, k
