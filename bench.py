@@ -263,10 +263,16 @@ def main():
         def step_dev():
             return stepper.step(rgb, dep, spa)
 
+        from gdn_pytorch_b200.data import HostBatchPrefetcher
+        feed = HostBatchPrefetcher(dev)
+
         def step_e2e():
-            r = rgb_h.to(dev, non_blocking=True)
-            d = dep_h.to(dev, non_blocking=True)
-            s = spa_h.to(dev, non_blocking=True)
+            # public API: pinned host batch -> HostBatchPrefetcher (H2D of the NEXT step's inputs on a copy stream, every
+            # step, inside the timed region) -> RtoDTrainStep.step -> D2H read of this step's loss
+            if feed.head == feed.tail:
+                feed.submit(rgb_h, dep_h, spa_h)
+            r, d, s = feed.next()
+            feed.submit(rgb_h, dep_h, spa_h)
             return float(stepper.step(r, d, s)["loss"])   # D2H read of the loss
         h2d = (rgb_h.numel() + dep_h.numel() + spa_h.numel()) * 4
         d2h = 8

@@ -78,3 +78,60 @@ class DeviceInputPipeline:
                 t = torch.from_numpy(np.ascontiguousarray(t))
             outs.append(preprocess_u8(t.to(self.device, non_blocking=True), flip, crop))
         return tuple(outs)
+
+
+class HostBatchPrefetcher:
+    """Double-buffered host->device feed for the fused steps: while step i runs, the inputs of step i+1 are copied
+    from (pinned) host memory on a dedicated copy stream, so the H2D transfer and its enqueue cost leave the step's
+    critical path (the reference does ``.cuda()`` synchronously at the top of every iteration, trainer.py:686-690).
+
+        feed = HostBatchPrefetcher(dev); feed.submit(*first_batch)
+        for nxt in batches:
+            x = feed.next(); feed.submit(*nxt); step.step(*x)
+
+    Slots are recycled: a slot is overwritten only after everything that was enqueued on the consumer's stream up to
+    the following ``next()`` has finished (event recorded there), i.e. after the step that read it."""
+
+    def __init__(self, device, depth=2):
+        self.dev = torch.device(device)
+        self.depth = max(2, int(depth))
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.slots = [None] * self.depth
+        self.ready = [None] * self.depth        # copy finished (recorded on the copy stream)
+        self.consumed = [None] * self.depth     # reader finished (recorded on the consumer's stream)
+        self.head = self.tail = 0               # next slot to fill / to hand out
+        self._last = None
+
+    def submit(self, *host_tensors):
+        if self.head - self.tail >= self.depth:
+            raise RuntimeError("HostBatchPrefetcher: %d batches already in flight" % self.depth)
+        i = self.head % self.depth
+        bufs = self.slots[i]
+        if bufs is None or any((b is None) != (t is None) or (t is not None and (b.shape != t.shape or b.dtype != t.dtype))
+                               for b, t in zip(bufs, host_tensors)) or len(bufs) != len(host_tensors):
+            bufs = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in host_tensors]
+            self.slots[i] = bufs
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[i] is not None:
+                self.copy_stream.wait_event(self.consumed[i])
+            for b, t in zip(bufs, host_tensors):
+                if t is not None:
+                    b.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ready[i] = ev
+        self.head += 1
+
+    def next(self):
+        if self.tail >= self.head:
+            raise RuntimeError("HostBatchPrefetcher: nothing submitted")
+        cur = torch.cuda.current_stream(self.dev)
+        if self._last is not None:              # whatever read the previous slot has been enqueued by now
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.consumed[self._last] = ev
+        i = self.tail % self.depth
+        cur.wait_event(self.ready[i])
+        self._last = i
+        self.tail += 1
+        return tuple(self.slots[i])

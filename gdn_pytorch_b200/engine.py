@@ -516,11 +516,13 @@ class Engine:
         side = self.side_stream
         self._fwd_wait = None
         if (side is not None and self.train and getattr(self, "async_fwd_pack", False)
-                and os.environ.get("GDN_ASYNC_FWD_PACK", "1") != "0"):
-            # fused training steps: the forward packs run on the side stream in order of first use, the forward
-            # plan waits for each pack just before the first convolution that reads it -- the big 3x3 / 512-channel
-            # tables (needed ~5 ms into the forward pass) are re-packed UNDER the first layers instead of in front
-            # of them (the re-pack was ~0.75 ms at the head of the step's critical chain)
+                and os.environ.get("GDN_ASYNC_FWD_PACK", "0") == "1"):
+            # EXPERIMENT, off by default: the forward packs run on the side stream in order of first use and the
+            # forward plan waits for each pack just before the first convolution that reads it, so that the big
+            # 3x3 / 512-channel tables are re-packed UNDER the first layers instead of in front of them (~0.75 ms at the
+            # head of the step).  Measured on the B200 (profiles/r01r_bench_{async,sync}pack.json, same box, back to
+            # back): 535.7 img/s with, 543.5 without -- the 28 k small pack CTAs delay the persistent conv CTAs of the
+            # first layers by more than the serial re-pack costs.  Kept for the next round (a faster pack kernel).
             main = torch.cuda.current_stream(self.dev)
             side.wait_stream(main)
             waits = {}

@@ -58,3 +58,24 @@ def test_pipeline_yields_what_the_training_step_consumes():
     pipe = DeviceInputPipeline(dev, train=True, seed=4)
     a, b, _ = pipe(torch.from_numpy(rgb[..., 0].copy()), torch.from_numpy(rgb), None)
     assert torch.equal(a[:, 0], b[:, 0])
+
+
+def test_host_batch_prefetcher_delivers_batches_in_order():
+    """double-buffered H2D feed: every batch arrives intact and in order while 'steps' run on the consumer stream"""
+    from gdn_pytorch_b200.data import HostBatchPrefetcher
+    feed = HostBatchPrefetcher("cuda")
+    batches = [(torch.full((4, 3, 32, 64), float(i)).pin_memory(), torch.full((4, 1, 32, 64), -float(i)).pin_memory(), None)
+               for i in range(7)]
+    feed.submit(*batches[0])
+    acc = torch.zeros((), device="cuda", dtype=torch.float64)
+    for i in range(7):
+        a, b, c = feed.next()
+        if i + 1 < 7:
+            feed.submit(*batches[i + 1])
+        assert c is None
+        torch.cuda._sleep(2_000_000)                       # a "step" that is still running when the next copy starts
+        acc += a.double().mean() * 10 + b.double().mean()
+        assert float(a[0, 0, 0, 0]) == float(i) and float(b[-1, 0, -1, -1]) == -float(i)
+    assert abs(float(acc) - sum(10 * i - i for i in range(7))) < 1e-9
+    with pytest.raises(RuntimeError):
+        feed.next()
