@@ -95,8 +95,8 @@ def test_rtod_step_with_guidance_gradient():
         ref = OL.rtod_loss(o, dep, spa, rgb, ft, ft_tar, guidance_grad=gg)
         (dout,) = torch.autograd.grad(ref["loss"], o)
         ref_dpre = dout * (1 - out * out)
-        assert abs(float(terms["latent_loss"]) - float(ref["latent_loss"])) <= 5e-3 * abs(float(ref["latent_loss"]))
-        assert abs(float(terms["loss"]) - float(ref["loss"])) <= 5e-3 * abs(float(ref["loss"]))
+        assert abs(float(terms["latent_loss"]) - float(ref["latent_loss"].detach())) <= 5e-3 * abs(float(ref["latent_loss"].detach()))
+        assert abs(float(terms["loss"]) - float(ref["loss"].detach())) <= 5e-3 * abs(float(ref["loss"].detach()))
         assert _l2rel(dpre, ref_dpre) <= (5e-2 if gg else 1e-4), (gg, _l2rel(dpre, ref_dpre))
         assert torch.isfinite(step.eng.flat_grad).all().item()
         res[gg] = (dpre, ref_dpre)
