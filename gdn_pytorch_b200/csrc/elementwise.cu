@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"
+#include "fold_rows.cuh"
+#include "pack_tile.cuh"
 
 namespace gdn {
 
@@ -281,20 +283,6 @@ __device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c
 }
 
 // source coordinate + weight of F.interpolate(scale_factor=2, mode='bilinear')
-__device__ __forceinline__ void up_coord(int o, int in, int mode, int& i0, int& i1, float& w1) {
-  float src;
-  if (mode == 1) {
-    src = (o + 0.5f) * 0.5f - 0.5f;
-    if (src < 0.f) src = 0.f;
-  } else {
-    src = in > 1 ? o * (float)(in - 1) / (float)(2 * in - 1) : 0.f;
-  }
-  i0 = (int)src;
-  if (i0 > in - 1) i0 = in - 1;
-  i1 = i0 + (i0 < in - 1 ? 1 : 0);
-  w1 = src - (float)i0;
-}
-
 __global__ void act_forward_kernel(const ActFwd a) {
   const int cg = a.C / 8;
   const long long n_f32 = a.out_f32 ? (long long)a.N * a.H * a.W * cg : 0;
@@ -775,25 +763,6 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
 }
 
 // -------------------------------------------------------------------------------------------- fold grad
-struct FoldK {
-  const float* dpad;   // fp32 [N][OH+2P][OW+2P][ctot]: gradient w.r.t. the conv's input buffer
-  int ctot, c_off;
-  int N, H, W, C;      // source activation extent
-  int P, reflect, up, dilate;
-  float* dact;         // fp32 [N][H][W][C]
-  int accumulate;
-};
-
-__device__ __forceinline__ int mirror_set(int Y, int OH, int P, int reflect, int* out) {
-  int n = 0;
-  out[n++] = Y + P;
-  if (reflect) {
-    if (Y >= 1 && Y <= P) out[n++] = P - Y;
-    if (Y >= OH - 1 - P && Y <= OH - 2) out[n++] = P + 2 * (OH - 1) - Y;
-  }
-  return n;
-}
-
 __global__ void fold_grad_kernel(const FoldK f) {
   const int cg = f.C / 4;
   const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
@@ -946,6 +915,30 @@ __global__ void __launch_bounds__(kEwThreads) fold_rows_kernel(const FoldK f, co
   }
 }
 
+// second version: the column candidates / weights of every source column are tabulated ONCE per CTA in shared memory
+// (they do not depend on the row or the channel), the per-item loop is loads + FMAs only.  The first version spent
+// its time recomputing them per item (ALU-bound at ~1 TB/s effective on the x2-bilinear adjoints).  Same accumulation
+// order, bit-identical results.  Dynamic shared memory: W * 64 bytes.
+__global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
+  extern __shared__ __align__(16) unsigned char s_fold[];
+  int* s_pc = reinterpret_cast<int*>(s_fold);                                  // [W][12]
+  float* s_qw = reinterpret_cast<float*>(s_fold + (size_t)f.W * kFoldColInts * sizeof(int));   // [W][4]
+  __shared__ int s_prow[12];
+  __shared__ float s_pw[12];
+  __shared__ int s_np;
+  const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
+  const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
+  for (int x = threadIdx.x; x < f.W; x += kEwThreads) fold_col_entry(f, OW, x, s_pc + x * kFoldColInts, s_qw + x * 4);
+  const int items = f.W << lg_cg;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_np = fold_row_entry(f, OH, row % f.H, s_prow, s_pw);
+    __syncthreads();
+    const int np = s_np;
+    for (int it = threadIdx.x; it < items; it += kEwThreads) fold_item(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc, s_qw);
+  }
+}
+
 // ---- backward through a FROZEN (eval-mode, BatchNorm folded) unit: dy = g * [y > 0] * scale[c] as bf16.
 // y is the unit's own post-ReLU output (fp32 stream or plain bf16 buffer); the folded BatchNorm scale is applied to the
 // gradient here so that the input-gradient convolution can use the un-folded weight pack.
@@ -1012,12 +1005,6 @@ __global__ void fold_thin_kernel(const FoldK f) {
 // -------------------------------------------------------------------------------- weight pack / unpack
 // packed[t][a][b] (t = r*kw + s, a < A, b < B) <-> w[a*sa + b*sb + r'*sr + s'*ss], (r', s') flipped when flip.
 // For im2col'd layers (col_c > 0): packed[0][a][k], k = (r*kw + s)*col_c + c  <->  w[a*sa + c*sb + r*sr + s*ss].
-struct PackK {
-  int kh, kw, A, B, Apad, Bpad;
-  long long sa, sb, sr, ss;
-  int flip, col_c;
-};
-
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
                                     __nv_bfloat16* __restrict__ out, const PackK k) {
   const int T = k.col_c ? 1 : k.kh * k.kw;
@@ -1121,7 +1108,17 @@ struct PackJob {
   const float* scale_a;
   __nv_bfloat16* out;
   int cta0, tiles_x;
+  int tb;            // b-tile width of the wide-tile version (pack_tile.cuh); 0 = first version (16 x 16 tiles)
 };
+
+__global__ void __launch_bounds__(256) pack_tile2_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
+                                                        __nv_bfloat16* __restrict__ out, const PackK k, const int tb) {
+  extern __shared__ float s_tile[];
+  const int a0 = blockIdx.y * kPackTA, b0 = blockIdx.x * tb;
+  pack_v2_phase1(w, k, a0, b0, tb, s_tile, threadIdx.x, blockDim.x);
+  __syncthreads();
+  pack_v2_phase2(scale_a, out, k, a0, b0, tb, s_tile, threadIdx.x, blockDim.x);
+}
 
 __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restrict__ jobs, const int njobs) {
   extern __shared__ float s_tile[];
@@ -1136,6 +1133,13 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restri
   }
   __syncthreads();
   const int tile = blockIdx.x - job.cta0;
+  if (job.tb > 0) {
+    const int a0 = (tile / job.tiles_x) * kPackTA, b0 = (tile % job.tiles_x) * job.tb;
+    pack_v2_phase1(job.w, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
+    __syncthreads();
+    pack_v2_phase2(job.scale_a, job.out, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
+    return;
+  }
   pack_tile_body(job.w, job.scale_a, job.out, job.k, (tile / job.tiles_x) * kPackTile, (tile % job.tiles_x) * kPackTile, s_tile);
 }
 
@@ -1166,6 +1170,12 @@ __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restric
     const float v = s_tile[(al * kPackTile + bl) * (T + 1) + tap];
     if (accumulate) *g += v; else *g = v;
   }
+}
+
+static bool pack_v1() {   // GDN_PACK_V1=1: the first version of the tile kernels (16 x 16 tiles), A/B knob
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GDN_PACK_V1"); v = (e && atoi(e) == 1) ? 1 : 0; }
+  return v == 1;
 }
 
 static bool pack_tileable(const PackK& k) {
@@ -1383,6 +1393,14 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
     const int lg = ew_lg2(f.C / 4);
     if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
       const int rows = f.N * f.H;
+      const size_t smem = (size_t)f.W * (kFoldColInts * sizeof(int) + 4 * sizeof(float));
+      static int v1 = -1;                       // GDN_FOLD_V1=1: the first version of the kernel (A/B knob)
+      if (v1 < 0) { const char* e = getenv("GDN_FOLD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }
+      if (!v1 && smem <= 40 * 1024) {
+        fold_rows2_kernel<<<ew_row_grid(rows), kEwThreads, smem, (cudaStream_t)stream>>>(f, lg, rows);
+        GDN_LAUNCH_CHECK("fold_rows2_kernel");
+        return GDN_OK;
+      }
       fold_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(f, lg, rows);
       GDN_LAUNCH_CHECK("fold_rows_kernel");
       return GDN_OK;
@@ -1430,6 +1448,18 @@ GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float
       GDN_CUDA_CHECK(cudaFuncSetAttribute(unpack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured[dev] = true;
     }
+    if (!pack_v1()) {
+      static bool configured2[64] = {false};
+      if (dev >= 0 && dev < 64 && !configured2[dev]) {
+        GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured2[dev] = true;
+      }
+      const int tb = pack_tb_for_taps(T);
+      dim3 grid2((k.Bpad + tb - 1) / tb, (k.Apad + kPackTA - 1) / kPackTA);
+      pack_tile2_kernel<<<grid2, 256, pack_smem_bytes(T), (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k, tb);
+      GDN_LAUNCH_CHECK("pack_tile2_kernel");
+      return GDN_OK;
+    }
     dim3 grid((k.Bpad + kPackTile - 1) / kPackTile, (k.Apad + kPackTile - 1) / kPackTile);
     pack_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
     GDN_LAUNCH_CHECK("pack_tile_kernel");
@@ -1457,8 +1487,15 @@ GDN_API int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const floa
   j.scale_a = scale_a;
   j.out = (__nv_bfloat16*)out;
   j.cta0 = cta0;
-  j.tiles_x = (j.k.Bpad + kPackTile - 1) / kPackTile;
-  *n_ctas = j.tiles_x * ((j.k.Apad + kPackTile - 1) / kPackTile);
+  if (pack_v1()) {
+    j.tb = 0;
+    j.tiles_x = (j.k.Bpad + kPackTile - 1) / kPackTile;
+    *n_ctas = j.tiles_x * ((j.k.Apad + kPackTile - 1) / kPackTile);
+  } else {
+    j.tb = pack_tb_for_taps(j.k.kh * j.k.kw);
+    j.tiles_x = (j.k.Bpad + j.tb - 1) / j.tb;
+    *n_ctas = j.tiles_x * ((j.k.Apad + kPackTA - 1) / kPackTA);
+  }
   memcpy(job_out, &j, sizeof(j));
   return GDN_OK;
 }
@@ -1467,7 +1504,10 @@ GDN_API int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const floa
 GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int max_taps, gdn_stream stream) {
   if (!jobs_dev || njobs <= 0 || total_ctas <= 0 || max_taps <= 0 || max_taps > kPackMaxTaps)
     return fail(GDN_INVALID_DESC, "gdn_pack_weights_table: bad arguments");
-  const size_t smem = (size_t)kPackTile * kPackTile * (max_taps + 1) * sizeof(float);
+  // every job of one table has max_taps taps (the caller groups by kernel size); the wide-tile version sizes its tile
+  // by the tap count, the first version is 16 x 16 x (taps + 1)
+  size_t smem = (size_t)kPackTile * kPackTile * (max_taps + 1) * sizeof(float);
+  if (!pack_v1() && pack_smem_bytes(max_taps) > smem) smem = pack_smem_bytes(max_taps);
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
