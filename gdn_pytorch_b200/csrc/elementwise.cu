@@ -1507,7 +1507,9 @@ GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ct
   // every job of one table has max_taps taps (the caller groups by kernel size); the wide-tile version sizes its tile
   // by the tap count, the first version is 16 x 16 x (taps + 1)
   size_t smem = (size_t)kPackTile * kPackTile * (max_taps + 1) * sizeof(float);
-  if (!pack_v1() && pack_smem_bytes(max_taps) > smem) smem = pack_smem_bytes(max_taps);
+  if (!pack_v1())
+    for (int t = 1; t <= max_taps; t++)      // a table may mix tap counts <= max_taps; the tile size is not monotonic in t
+      if (pack_smem_bytes(t) > smem) smem = pack_smem_bytes(t);
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);

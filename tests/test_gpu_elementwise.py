@@ -278,7 +278,8 @@ def test_pack_weights_table_matches_per_tensor_packs():
         buf, n = C.create_string_buffer(jsz), C.c_int(0)
         _lib.check(L.gdn_pack_job_fill(C.byref(pd), C.c_void_p(w.data_ptr()), sp, C.c_void_p(out.data_ptr()), cta0, buf,
                                        C.byref(n)), "job_fill")
-        assert n.value == ((cin + 15) // 16) * ((cout + 15) // 16)
+        tb = 64 if kk <= 9 else (32 if kk <= 25 else 16)       # wide-tile version: 16 (a) x tb (b) tiles, pack_tile.cuh
+        assert n.value in (((cin + 15) // 16) * ((cout + 15) // 16), ((cin + tb - 1) // tb) * ((cout + 15) // 16))
         blobs.append(buf.raw)
         cta0 += n.value
         outs.append(out)
