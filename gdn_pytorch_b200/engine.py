@@ -225,6 +225,14 @@ class Engine:
                 except Exception as e:
                     raise RuntimeError("gdn_b200: kernel failure in '%s' (algo 0x%x): %s" % (what, getattr(desc, "algo", 0), e))
         run.label = what
+        # algorithmic work of tensor-core launches (2*M*N*K with the real channel counts), for tools/profile_ops.py
+        if fn is L.gdn_conv2d:
+            cin = desc.src0.c + (desc.src1.c if desc.src1.ptr else 0)
+            run.flops = 2.0 * desc.src0.n * desc.out_h * desc.out_w * desc.cout * cin * desc.kh * desc.kw
+            run.tiles = (desc.src0.n * desc.out_h * desc.out_w + 127) // 128
+        elif fn is L.gdn_conv2d_wgrad:
+            cin = desc.x0.c + (desc.x1.c if desc.x1.ptr else 0)
+            run.flops = 2.0 * desc.x0.n * desc.out_h * desc.out_w * desc.cout_pad * cin * desc.kh * desc.kw
         return run
 
     def _pack_call(self, pd, wt, scale, out, what, w_off=0):
@@ -1066,8 +1074,9 @@ class Engine:
             d.algo = cache[key]
             self.algo_choice[what] = d.algo
 
-    def profile(self, ops, reps=3):
-        """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid"""
+    def profile(self, ops, reps=3, with_flops=False):
+        """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid.
+        with_flops: rows are (label, ms, flops or None, 128-pixel tiles or None)"""
         s = _lib.stream_ptr()
         evs = []
         for op in ops:
@@ -1078,6 +1087,9 @@ class Engine:
             e1.record()
             evs.append((getattr(op, "label", "misc"), e0, e1))
         torch.cuda.synchronize()
+        if with_flops:
+            return [(n, a.elapsed_time(b) / reps, getattr(op, "flops", None), getattr(op, "tiles", None))
+                    for (n, a, b), op in zip(evs, ops)]
         return [(n, a.elapsed_time(b) / reps) for n, a, b in evs]
 
     def backward(self, dpre=None, dout_nhwc=None):

@@ -102,3 +102,54 @@ def test_bucketed_allreduce_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
+
+
+def test_device_validator_result_host_logic():
+    """validate()'s bookkeeping (/root/reference/src/trainer.py:62-87) on the rows the metric kernel fills: plain
+    averages, the 'min_errors' pass (rows visited by increasing abs_diff -- same sums, trainer.py:62-85) and the Make3D
+    column subset.  Host logic only: the rows are written by hand instead of by the kernel."""
+    from gdn_pytorch_b200.validate import DeviceValidator, ERROR_NAMES
+    rows = torch.tensor([[3.0, 0.3, 0.03, 0.7, 0.8, 0.9, 5.0, 0.5],
+                         [1.0, 0.1, 0.01, 0.9, 0.95, 0.99, 3.0, 0.3],
+                         [2.0, 0.2, 0.02, 0.8, 0.9, 0.95, 4.0, 0.4]], dtype=torch.float64)
+    for dataset in ("KITTI", "NYU", "Make3D"):
+        v = DeviceValidator.__new__(DeviceValidator)
+        v.rows, v.n, v.dataset, v.group = torch.zeros((8, 8), dtype=torch.float64), 3, dataset, None
+        v.rows[:3] = rows
+        avg, mins, names = v.result()
+        cols = [0, 1, 2, 6] if dataset == "Make3D" else list(range(8))
+        assert names == ERROR_NAMES[dataset] and len(avg) == len(cols) == len(mins)
+        for i, c in enumerate(cols):
+            assert abs(avg[i] - rows[:, c].mean().item()) < 1e-12
+            assert abs(mins[i] - avg[i]) < 1e-12
+    v.n = 0
+    avg, _, _ = v.result()
+    assert avg == [0.0] * 4
+
+
+_VAL_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from gdn_pytorch_b200.validate import DeviceValidator
+rank = int(sys.argv[1])
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[2]
+dist.init_process_group("gloo", rank=rank, world_size=2)
+v = DeviceValidator.__new__(DeviceValidator)
+v.rows, v.n, v.dataset, v.group = torch.zeros((4, 8), dtype=torch.float64), 2, "KITTI", None
+v.rows[0] = float(rank + 1); v.rows[1] = float(10 * (rank + 1))
+avg, mins, names = v.result()          # per-batch rows of both ranks are gathered: mean over 4 rows
+assert all(abs(a - (1 + 10 + 2 + 20) / 4.0) < 1e-12 for a in avg), avg
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_device_validator_gathers_rows_across_ranks_gloo_world2(tmp_path):
+    script = tmp_path / "v.py"
+    script.write_text(_VAL_WORKER % ROOT)
+    port = str(29900 + os.getpid() % 90)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()
