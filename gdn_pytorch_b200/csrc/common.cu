@@ -84,3 +84,33 @@ GDN_API const char* gdn_last_error(void) { return gdn::g_err; }
 GDN_API int gdn_version(void) { return 100; }
 GDN_API int gdn_sm_count(void) { return gdn::device_sm_count(); }
 }
+
+// ---- entry-point names of the coverage contract ------------------------------------------------
+// The contract lists the hot-path entry points by operation (conv fwd / dgrad / wgrad, BN+activation apply and its
+// backward, the two losses, the feature MSE, workspace query).  The library implements several of them with ONE
+// descriptor-driven function (forward and input-gradient convolutions are the same implicit GEMM on different packs;
+// the two losses differ by `mode`), and keeps every pointer inside the descriptor instead of in the argument list.
+// These aliases export the contract's names on top of that; they add no code path of their own.
+extern "C" {
+GDN_API int gdn_conv2d_fwd(const gdn_conv_desc* d, gdn_stream stream) { return gdn_conv2d(d, stream); }
+GDN_API int gdn_conv2d_dgrad(const gdn_conv_desc* d, gdn_stream stream) { return gdn_conv2d(d, stream); }
+GDN_API int gdn_bn_act_apply(const gdn_act_fwd_desc* d, gdn_stream stream) { return gdn_act_forward(d, stream); }
+GDN_API int gdn_bn_act_apply_bwd(const gdn_bn_bwd_desc* d, gdn_stream stream) { return gdn_act_backward(d, stream); }
+GDN_API int gdn_loss_rtod_fwd_bwd(const gdn_loss_desc* d, gdn_stream stream) {
+  if (!d) return gdn::fail(GDN_INVALID_DESC, "gdn_loss_rtod_fwd_bwd: null descriptor");
+  gdn_loss_desc c = *d;
+  c.mode = 0;
+  return gdn_loss(&c, stream);
+}
+GDN_API int gdn_loss_dtod_fwd_bwd(const gdn_loss_desc* d, gdn_stream stream) {
+  if (!d) return gdn::fail(GDN_INVALID_DESC, "gdn_loss_dtod_fwd_bwd: null descriptor");
+  gdn_loss_desc c = *d;
+  c.mode = 1;
+  return gdn_loss(&c, stream);
+}
+GDN_API int gdn_feature_mse(const float* a, const float* b, int64_t n, double* out, gdn_stream stream) {
+  return gdn_sqdiff_sum(a, b, n, out, stream);
+}
+// the convolutions stage everything in shared / tensor memory and need no global workspace
+GDN_API size_t gdn_workspace_bytes(const gdn_conv_desc* d) { (void)d; return 0; }
+}

@@ -17,7 +17,7 @@
  *   gdn_bn_finalize       batch statistics -> scale/shift, running-stat update (nn.BatchNorm2d training mode)
  *   gdn_bn_bwd_reduce / gdn_act_backward   autograd of the above
  *   gdn_fold_grad         adjoint of reflection padding / bilinear x2 upsampling / zero-dilation
- *   gdn_loss_rtod / gdn_loss_dtod / gdn_feature_mse   src/trainer.py:433-456, 705-757; src/utils.py:105-178
+ *   gdn_loss (mode 0 = RtoD, 1 = DtoD) / gdn_sqdiff_sum (feature MSE)   src/trainer.py:433-456, 705-757; src/utils.py:105-178
  *   gdn_eigen_metrics     src/calculate_error.py:10-103
  *   gdn_adam_step         optim.Adam(lr, [0.9,0.999], eps=1e-8, weight_decay=5e-4): src/GDN_main.py:157,173
  *   gdn_pack_weights / gdn_unpack_wgrad   fp32 OIHW <-> bf16 [tap][Cout][Cin] operand layout (BN folding at eval)
@@ -291,6 +291,22 @@ int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
  * far (incremented by this call before use) -- lets a whole training step live in one captured CUDA graph. */
 int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, float* dyn, double beta1, double beta2,
                       float eps, float weight_decay, float grad_scale, gdn_stream stream);
+
+/* ---- the coverage contract's entry-point names -------------------------------------------------
+ * One descriptor-driven function implements several contract entries (forward and input-gradient convolutions are
+ * the same implicit GEMM on different weight packs; the two losses differ by `mode`); pointers travel in the
+ * descriptors.  These names are exported as aliases: gdn_conv2d_fwd = gdn_conv2d_dgrad = gdn_conv2d,
+ * gdn_bn_act_apply = gdn_act_forward, gdn_bn_act_apply_bwd = gdn_act_backward (after gdn_bn_bwd_reduce),
+ * gdn_loss_rtod_fwd_bwd / gdn_loss_dtod_fwd_bwd = gdn_loss with mode 0 / 1, gdn_feature_mse = gdn_sqdiff_sum,
+ * gdn_workspace_bytes = 0 (the convolutions need no global workspace). */
+int gdn_conv2d_fwd(const gdn_conv_desc* d, gdn_stream stream);
+int gdn_conv2d_dgrad(const gdn_conv_desc* d, gdn_stream stream);
+int gdn_bn_act_apply(const gdn_act_fwd_desc* d, gdn_stream stream);
+int gdn_bn_act_apply_bwd(const gdn_bn_bwd_desc* d, gdn_stream stream);
+int gdn_loss_rtod_fwd_bwd(const gdn_loss_desc* d, gdn_stream stream);
+int gdn_loss_dtod_fwd_bwd(const gdn_loss_desc* d, gdn_stream stream);
+int gdn_feature_mse(const float* a, const float* b, int64_t n, double* out, gdn_stream stream);
+size_t gdn_workspace_bytes(const gdn_conv_desc* d);
 
 const char* gdn_last_error(void);
 int gdn_version(void);
