@@ -20,10 +20,21 @@ def _require_cuda(x):
 
 
 def _check_norm(module):
-    for m in module.modules():
-        if isinstance(m, torch.nn.InstanceNorm2d):
-            raise NotImplementedError("gdn_b200: only norm='Batch' is implemented (the reference default, option.py:43; "
-                                      "no live configuration uses the InstanceNorm branch)")
+    """norm != 'Batch' builds nn.InstanceNorm2d(affine=True, track_running_stats=True) in the ConvBlocks / ConvTBlocks
+    (reference AE_model_unet.py:70-76, 88-93).  In eval mode such a layer normalises with its RUNNING statistics
+    (torch: use_input_stats = training or not track_running_stats), i.e. exactly like an eval-mode BatchNorm with the
+    same state_dict keys -- it folds into the weights like one, so inference works.  In train mode it needs
+    per-sample statistics, which no live configuration uses (option.py:43 defaults to Batch) and no kernel here
+    computes: that is an error, not a silent substitution."""
+    has_in = module.__dict__.get("_gdn_has_instance_norm")
+    if has_in is None:
+        has_in = any(isinstance(m, torch.nn.InstanceNorm2d) for m in module.modules())
+        module.__dict__["_gdn_has_instance_norm"] = has_in
+    if has_in and module.training:
+        raise NotImplementedError("gdn_b200: norm='Instance' is implemented for eval-mode inference only (running "
+                                  "statistics, like the reference in .eval()); train mode needs per-sample statistics "
+                                  "-- the reference default is norm='Batch' (option.py:43) and no live configuration "
+                                  "trains the InstanceNorm branch")
 
 
 def _engines(module):
@@ -113,6 +124,7 @@ def run_network(module, x, istrain):
         graph = module.gdn_graph()
         module.__dict__["_gdn_graph"] = graph
     _engines(module)
+    _check_norm(module)
     if x.dim() != 4 or x.shape[1] != graph.cin:
         raise ValueError("gdn_b200: expected input (N, %d, H, W), got %s" % (graph.cin, tuple(x.shape)))
     if x.shape[2] % 16 or x.shape[3] % 16:
@@ -144,6 +156,7 @@ def encoder_features(module, x):
         graph = module.gdn_graph()
         module.__dict__["_gdn_graph"] = graph
     _engines(module)
+    _check_norm(module)
     names = graph.encoder_outputs
     eng = get_engine(module, graph, x, train=module.training, backward=False, want=names, stop_after=names[-1])
     with torch.no_grad():
@@ -199,6 +212,7 @@ def run_block(block, x):
         graph = _block_graph(block)
         block.__dict__["_gdn_graph"] = graph
     _engines(block)
+    _check_norm(block)
     if graph.cin < 64 and x.requires_grad:
         raise NotImplementedError("gdn_b200: input gradients of thin-channel (first-layer) blocks are not needed by the "
                                   "reference path and not implemented")

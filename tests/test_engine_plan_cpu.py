@@ -138,3 +138,64 @@ def test_training_plan_forward_backward_matches_autograd(gname):
         assert _l2rel(eng.grad[k], v.grad.float()) <= 3e-2, k
         checked += 1
     assert checked >= 2 * len(g.units) - 2
+
+
+def test_instance_norm_branch_eval_is_running_stat_normalisation():
+    """norm != 'Batch' (reference AE_model_unet.py:70-76, 88-93): nn.InstanceNorm2d(affine=True,
+    track_running_stats=True) in eval mode == eval-mode BatchNorm on the same state_dict -- what lets the engine fold it"""
+    g = torch.Generator().manual_seed(0)
+    inn = torch.nn.InstanceNorm2d(8, affine=True, track_running_stats=True)
+    bn = torch.nn.BatchNorm2d(8, affine=True, track_running_stats=True)
+    with torch.no_grad():
+        inn.weight.copy_(torch.rand(8, generator=g) + 0.5)
+        inn.bias.copy_(torch.rand(8, generator=g) - 0.5)
+        inn.running_mean.copy_(torch.rand(8, generator=g) - 0.5)
+        inn.running_var.copy_(torch.rand(8, generator=g) + 0.5)
+    bn.load_state_dict(inn.state_dict())
+    x = torch.randn((3, 8, 5, 7), generator=g)
+    assert torch.allclose(inn.eval()(x), bn.eval()(x), atol=1e-6)
+    assert not torch.allclose(inn.train()(x), bn.eval()(x), atol=1e-3)      # train mode: per-sample statistics
+
+
+def test_instance_norm_autoencoder_inference_plan(monkeypatch):
+    """--norm Instance reaches nn.InstanceNorm2d only in the ``AutoEncoder`` class (reference AE_model_unet.py:146-154:
+    AutoEncoder_2 / _DtoD print the choice but build their blocks with the default) -- the inference-only class of the
+    live code.  Same state_dict keys; eval-mode inference through the engine (emulated ABI) against the UNMODIFIED
+    reference class when /root/reference is present, else the oracle; train mode is refused (per-sample statistics are
+    not implemented -- no silent substitution)."""
+    import contextlib, io
+    from gdn_pytorch_b200.engine import Engine
+    from gdn_pytorch_b200.module_runtime import _params, _check_norm
+    from oracle import model as OM, synth
+    from oracle.refimport import reference_available, load_reference
+    m = build_module("AutoEncoder", norm="Instance", init_weights=False, height=H, width=W)
+    assert sum(isinstance(t, torch.nn.InstanceNorm2d) for t in m.modules()) == 7
+    assert not any(isinstance(t, torch.nn.InstanceNorm2d)
+                   for t in build_module("AutoEncoder_2", norm="Instance", init_weights=False).modules())
+    sd = synth.synth_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed=5)
+    m.load_state_dict(sd)
+    x = synth.synth_rgb(B, H, W, 2)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        _check_norm(m)
+    m.eval()
+    _check_norm(m)
+    if reference_available():
+        ae = load_reference()[0]
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = ae.AutoEncoder(norm="Instance", height=H, width=W)
+        assert list(ref.state_dict().keys()) == list(m.state_dict().keys())
+        ref.load_state_dict({k: v.clone() for k, v in sd.items()})
+        ref.eval()
+        monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)     # AutoEncoder.forward: x.cuda() (:161)
+        with torch.no_grad():
+            want = ref(x, istrain=False)
+        monkeypatch.undo()
+    else:
+        want = OM.autoencoder(sd, x, istrain=False)
+    with emulated_abi():
+        g = m.gdn_graph()
+        eng = Engine(g, _params(m), B, H, W, train=False, device=torch.device("cpu"))
+        engine_forward(eng, x)
+        got = eng.depth()
+    assert relerr(got, want) <= 1e-2, relerr(got, want)
