@@ -2,6 +2,7 @@
 the ABI (tests/abi_emulator.py) against the real kernels on whole engine plans -- the emulator is what the CPU suite
 trusts for plan checks, so it is pinned here on the hardware it stands in for."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -142,3 +143,44 @@ def test_abi_emulator_agrees_with_the_kernels(gname, train):
         a, b = eng.flat_grad.cpu(), emu.flat_grad
         cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
         assert cos >= 0.97 and _l2(a, b) <= 0.25, (cos, _l2(a, b))
+
+
+@pytest.mark.skipif(os.environ.get("GDN_EPI_T") != "1", reason="experiment: run with GDN_EPI_T=1 (transposed fp32 epilogue)")
+@pytest.mark.parametrize("cin,cout,k,stride2dst,resid,algo", [(64, 64, 1, False, False, 0), (128, 64, 1, False, True, 0),
+                                                             (64, 128, 3, False, True, 2), (256, 256, 3, True, False, 1),
+                                                             (64, 64, 9, False, True, 2 | (4 << 8) | (1 << 24))])
+def test_transposed_fp32_epilogue_on_hardware(cin, cout, k, stride2dst, resid, algo):
+    """fp32-only outputs (what the input-gradient launches write): with GDN_EPI_T=1 the library routes them to
+    conv_igemm_kernel<.., EPI_T = true>; results must equal the fp64 reference like the default epilogue's"""
+    import torch.nn.functional as F
+    from gdn_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(cin + cout + k)
+    N, H, W = 2, 24, 40
+    p = k // 2
+    x = (torch.rand((N, cin, H, W), generator=g) * 2 - 1).to(dev).to(torch.bfloat16)
+    w = ((torch.rand((cout, cin, k, k), generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16)
+    ref = F.conv2d(x.double(), w.double(), None, 1, p)
+    xb = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous()
+    sy = 2 if stride2dst else 1
+    DH, DW = H * sy, W * sy
+    out = torch.full((N, DH, DW, cout), float("nan"), device=dev)
+    r = (torch.rand((N, DH, DW, cout), generator=g) - 0.5).to(dev) if resid else None
+    d = _lib.ConvDesc()
+    d.src0 = _lib.Act(xb.data_ptr(), N, H, W, cin, 0)
+    d.weights = wp.data_ptr()
+    d.kh = d.kw = k
+    d.stride = 1
+    d.off_y = d.off_x = -p
+    d.out_h, d.out_w, d.cout, d.cout_pad, d.algo = H, W, cout, cout, algo
+    d.resid = r.data_ptr() if resid else None
+    d.out_f32 = out.data_ptr()
+    d.dst_h, d.dst_w, d.dst_sy, d.dst_sx, d.dst_oy, d.dst_ox = DH, DW, sy, sy, sy - 1, 0
+    _lib.check(_lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
+    torch.cuda.synchronize()
+    got = out[:, sy - 1::sy, ::sy].permute(0, 3, 1, 2).double()
+    want = ref + (r[:, sy - 1::sy, ::sy].permute(0, 3, 1, 2).double() if resid else 0)
+    assert not torch.isnan(got).any()
+    assert (got - want).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    if stride2dst:                                   # positions between the strided destinations stay untouched
+        assert torch.isnan(out[:, 0::2, 1::2]).all()
