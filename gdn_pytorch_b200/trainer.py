@@ -237,6 +237,10 @@ class _StepBase:
             if st is not None and st.data_ptr() != t.data_ptr():
                 st.copy_(t, non_blocking=True)
         self._graph.replay()
+        # the replayed Adam / BatchNorm-finalize kernels rewrote parameters and running statistics through raw pointers
+        # (no tensor _version bump, none of the Python bookkeeping of _optim_step / _after_train_forward runs):
+        # every OTHER engine of this module (cached eval-mode engines, DeviceValidator) must re-pack / re-fold
+        self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1
         return self._static_out
 
     # ------------------------------------------------------------------ checkpoint / resume

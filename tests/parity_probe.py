@@ -1,0 +1,228 @@
+"""Train-mode parity measurements at the headline shape (TEST INFRASTRUCTURE, run on the GPU box).
+
+    python -m tests.parity_probe [fwd] [grad] [traj]  [--b 4] [--h 128] [--w 416]
+
+Prints, for AutoEncoder_2 and AutoEncoder_DtoD in train mode (batch-statistics BatchNorm):
+  fwd   max-rel error of the B200 path against the fp32 oracle and against the bf16-emulating oracle
+        (oracle/model.py bf16=True rounds exactly where the device path rounds), next to the oracle's own
+        bf16-vs-fp32 distance (the conditioning of the comparison), at three weight states
+  grad  per-parameter-tensor cosine / relative L2 of the module API's .grad against torch autograd through the oracle
+  traj  N-step loss trajectory of the fused RtoD step against the same step restated with torch ops (fp32, TF32 off)
+tests/test_gpu_train_parity.py asserts bounds derived from these measurements (profiles/r02*_parity_probe.log).
+Reference: /root/reference/src/AE_model_unet.py:312-368,527-574; src/trainer.py:696-768.
+"""
+import argparse
+import sys
+
+import torch
+
+from oracle import losses as OL, model as OM, synth
+from tests.util import build_module, relerr, shapes_of
+
+dev = "cuda"
+
+
+def no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def inputs_for(name, b, h, w, seed):
+    return (synth.synth_rgb(b, h, w, seed) if name == "AutoEncoder_2" else synth.synth_depth(b, h, w, seed)).to(dev)
+
+
+def param_keys(sd):
+    return [k for k, v in sd.items() if v.dtype == torch.float32 and not k.endswith(("running_mean", "running_var"))]
+
+
+def state(name, kind, b, h, w, seed=0):
+    """kind: 'random' (BN affine randomised), 'init' (gamma 1, beta 0: the reference's _initialize_weights),
+    'warm' ('init' followed by a few fp32 oracle training steps towards a synthetic depth target)"""
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(shapes_of(name), seed=seed, bn_random=(kind == "random")).items()}
+    if kind == "warm":
+        sd = warm_up(name, sd, b, h, w)
+    return sd
+
+
+def warm_up(name, sd, b, h, w, steps=30, lr=2e-4):
+    no_tf32()
+    pk = param_keys(sd)
+    for k in pk:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in pk], lr, (0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    for i in range(steps):
+        x = inputs_for(name, b, h, w, 100 + i % 4)
+        tgt = synth.synth_depth(b, h, w, 100 + i % 4).to(dev)
+        out = OM.FORWARDS[name](sd, x, istrain=False, train=True, update_running=True)
+        loss = OL.berhu_masked(out, tgt, None)[0]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+def product_module(name, sd, h, w):
+    m = build_module(name, init_weights=False, height=h, width=w)
+    m.load_state_dict({k: v.detach().cpu() for k, v in sd.items()})
+    return m.to(dev)
+
+
+def probe_forward(name, kind, b, h, w):
+    no_tf32()
+    sd = state(name, kind, b, h, w)
+    x = inputs_for(name, b, h, w, 3)
+    with torch.no_grad():
+        r32 = OM.FORWARDS[name]({k: v.clone() for k, v in sd.items()}, x, istrain=False, train=True)
+        r16 = OM.FORWARDS[name]({k: v.clone() for k, v in sd.items()}, x, istrain=False, train=True, bf16=True)
+        m = product_module(name, sd, h, w)
+        m.train()
+        got = m(x, istrain=False)
+    res = {"vs_fp32": relerr(got, r32), "vs_bf16": relerr(got, r16), "bf16_vs_fp32": relerr(r16, r32),
+           "out_absmax": r32.abs().max().item(), "out_std": r32.std().item()}
+    print("fwd  %-17s %-6s B%d %dx%d  engine-vs-fp32 %.3e  engine-vs-bf16oracle %.3e  (bf16oracle-vs-fp32 %.3e)  |out|max %.3f std %.3f"
+          % (name, kind, b, h, w, res["vs_fp32"], res["vs_bf16"], res["bf16_vs_fp32"], res["out_absmax"], res["out_std"]), flush=True)
+    return res
+
+
+def oracle_grads(name, sd, x, tgt, bf16):
+    sdg = {k: v.detach().clone() for k, v in sd.items()}
+    pk = param_keys(sdg)
+    for k in pk:
+        sdg[k].requires_grad_(True)
+    out = OM.FORWARDS[name](sdg, x, istrain=False, train=True, bf16=bf16)
+    loss = ((out - tgt) ** 2).mean()
+    g = torch.autograd.grad(loss, [sdg[k] for k in pk])
+    return dict(zip(pk, g)), out.detach()
+
+
+def probe_grad(name, kind, b, h, w):
+    no_tf32()
+    sd = state(name, kind, b, h, w)
+    x = inputs_for(name, b, h, w, 3)
+    tgt = synth.synth_depth(b, h, w, 7).to(dev)
+    g32, _ = oracle_grads(name, sd, x, tgt, False)
+    g16, _ = oracle_grads(name, sd, x, tgt, True)
+    m = product_module(name, sd, h, w)
+    m.train()
+    out = m(x, istrain=False)
+    loss = ((out - tgt) ** 2).mean()
+    m.zero_grad()
+    loss.backward()
+    got = {k: p.grad.detach() for k, p in m.named_parameters()}
+
+    def cmp(a, b_):
+        a, b_ = a.flatten().double(), b_.flatten().double()
+        nb = b_.norm().item()
+        if nb < 1e-20:
+            return None
+        return (torch.dot(a, b_) / (a.norm() * b_.norm() + 1e-300)).item(), ((a - b_).norm() / nb).item()
+    rows = []
+    for k in got:
+        c32, c16, cc = cmp(got[k], g32[k]), cmp(got[k], g16[k]), cmp(g16[k], g32[k])
+        if c32 is None:
+            continue
+        rows.append((k, c32, c16, cc))
+    import statistics as st
+    for tag, idx in (("engine-vs-fp32", 1), ("engine-vs-bf16oracle", 2), ("bf16oracle-vs-fp32", 3)):
+        cos = [r[idx][0] for r in rows]
+        l2 = [r[idx][1] for r in rows]
+        worst = min(rows, key=lambda r: r[idx][0])
+        print("grad %-17s %-6s %-22s cos min %.4f med %.4f | L2 max %.3e med %.3e | worst %s"
+              % (name, kind, tag, min(cos), st.median(cos), max(l2), st.median(l2), worst[0]), flush=True)
+    # whole-gradient figures (all tensors concatenated)
+    cat = lambda d: torch.cat([d[k].flatten().double() for k, *_ in rows])
+    a, b32, b16 = cat(got), cat(g32), cat(g16)
+    print("grad %-17s %-6s whole: cos(fp32) %.5f L2(fp32) %.3e | cos(bf16) %.5f L2(bf16) %.3e"
+          % (name, kind, (torch.dot(a, b32) / (a.norm() * b32.norm())).item(), ((a - b32).norm() / b32.norm()).item(),
+             (torch.dot(a, b16) / (a.norm() * b16.norm())).item(), ((a - b16).norm() / b16.norm()).item()), flush=True)
+    return rows
+
+
+class TorchRtoDStep:
+    """trainer.py:696-768 with torch ops (oracle restatement), fp32 or bf16-emulating forward; the reference for
+    the trajectory test"""
+
+    def __init__(self, sd, sdd, lr, bf16=False):
+        self.sd = {k: v.detach().clone() for k, v in sd.items()}
+        self.sdd = sdd
+        self.bf16 = bf16
+        pk = param_keys(self.sd)
+        for k in pk:
+            self.sd[k].requires_grad_(True)
+        self.opt = torch.optim.Adam([self.sd[k] for k in pk], lr, (0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+
+    def step(self, rgb, dep, spa):
+        out = OM.autoencoder_2(self.sd, rgb, istrain=False, train=True, update_running=True, bf16=self.bf16)
+        with torch.no_grad():
+            ft_tar = OM.autoencoder_dtod(self.sdd, dep, encoder_only=True)
+            ft = OM.autoencoder_dtod(self.sdd, out, encoder_only=True)
+        terms = OL.rtod_loss(out, dep, spa, rgb, ft, ft_tar)
+        self.opt.zero_grad(set_to_none=True)
+        terms["loss"].backward()
+        self.opt.step()
+        return {k: float(v) for k, v in terms.items()}
+
+
+def probe_traj(b, h, w, steps=50, lr=2e-5, kind="init", nbatch=4):
+    from gdn_pytorch_b200.trainer import RtoDTrainStep
+    no_tf32()
+    sd = state("AutoEncoder_2", kind, b, h, w, seed=0)
+    sdd = {k: v.to(dev) for k, v in synth.synth_state_dict(shapes_of("AutoEncoder_DtoD"), seed=1).items()}
+    batches = []
+    for i in range(nbatch):
+        dep = synth.synth_depth(b, h, w, i)
+        batches.append((synth.synth_rgb(b, h, w, i).to(dev), dep.to(dev), synth.synth_sparse(dep, i).to(dev)))
+    ref = TorchRtoDStep(sd, sdd, lr)
+    ref16 = TorchRtoDStep(sd, sdd, lr, bf16=True)
+    rtod = product_module("AutoEncoder_2", sd, h, w)
+    dtod = product_module("AutoEncoder_DtoD", sdd, h, w).eval()
+    rtod.train()
+    st = RtoDTrainStep(rtod, dtod, lr=lr)
+    worst = {"loss": 0.0, "output_loss": 0.0, "smooth_loss": 0.0, "latent_loss": 0.0}
+    worst16 = dict(worst)
+    for i in range(steps):
+        bt = batches[i % nbatch]
+        a = {k: float(v) for k, v in st.step(*bt).items()}
+        r = ref.step(*bt)
+        r16 = ref16.step(*bt)
+        for k in worst:
+            worst[k] = max(worst[k], abs(a[k] - r[k]) / (abs(r[k]) + 1e-12))
+            worst16[k] = max(worst16[k], abs(r16[k] - r[k]) / (abs(r[k]) + 1e-12))
+        if i < 5 or i % 10 == 9:
+            print("traj step %2d  product loss %.6f (out %.6f lat %.6f sm %.6f) | torch-fp32 %.6f (out %.6f lat %.6f sm %.6f) | torch-bf16emu %.6f"
+                  % (i, a["loss"], a["output_loss"], a["latent_loss"], a["smooth_loss"], r["loss"], r["output_loss"],
+                     r["latent_loss"], r["smooth_loss"], r16["loss"]), flush=True)
+    print("traj %s B%d %dx%d %d steps lr %g: worst relative deviation product-vs-fp32 %s ; bf16emu-vs-fp32 %s"
+          % (kind, b, h, w, steps, lr, {k: "%.3e" % v for k, v in worst.items()}, {k: "%.3e" % v for k, v in worst16.items()}), flush=True)
+    # parameters after the trajectory
+    pr = dict(rtod.named_parameters())
+    num = sum(((pr[k].detach() - ref.sd[k].detach()).double() ** 2).sum().item() for k in pr)
+    den = sum(((ref.sd[k].detach() - sd[k]).double() ** 2).sum().item() for k in pr)
+    print("traj parameter drift: |p_product - p_ref| / |p_ref - p_0| = %.3e" % ((num / max(den, 1e-300)) ** 0.5), flush=True)
+    return worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="*", default=["fwd", "grad", "traj"])
+    ap.add_argument("--b", type=int, default=4)
+    ap.add_argument("--h", type=int, default=128)
+    ap.add_argument("--w", type=int, default=416)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--kinds", default="random,init,warm")
+    a = ap.parse_args()
+    kinds = a.kinds.split(",")
+    for name in ("AutoEncoder_2", "AutoEncoder_DtoD"):
+        for kind in kinds:
+            if "fwd" in a.what:
+                probe_forward(name, kind, a.b, a.h, a.w)
+            if "grad" in a.what:
+                probe_grad(name, kind, a.b, a.h, a.w)
+    if "traj" in a.what:
+        for kind in kinds:
+            if kind != "random":
+                probe_traj(a.b, a.h, a.w, a.steps, kind=kind)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
