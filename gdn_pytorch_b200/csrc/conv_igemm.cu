@@ -62,7 +62,6 @@ struct ConvK {
   int cout, cout_pad;
   double* stat_sum;
   double* stat_sq;
-  int epi_t;                 // fp32-only outputs: transpose the accumulator block across the warp and store whole 128-byte runs
 };
 
 struct Ring {
@@ -109,23 +108,7 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[NV], int lane) {
   return v[0];
 }
 
-// In-register 32 x 32 transpose across a warp: before, lane l holds row l (v[i] = M[l][i]); after, lane l holds
-// column l (v[i] = M[i][l]).  5 butterfly stages of 16 exchanges.
-__device__ __forceinline__ void lane_transpose32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-      if (i & s) continue;
-      float x = up ? v[i] : v[i | s];
-      x = __shfl_xor_sync(0xffffffffu, x, s);
-      if (up) v[i] = x; else v[i | s] = x;
-    }
-  }
-}
-
-template <int BN, int CG, bool EPI_T = false>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvK p) {
@@ -423,33 +406,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               atomicAdd(&s_stat[1][cc + lane], t2);
             }
           }
-          if constexpr (EPI_T && CW == 32) {      // separate instantiation: the default kernels compile exactly as before
-            if (p.epi_t) {
-              // fp32-only epilogue (input-gradient launches: no bf16 copy, no statistics, cout % 32 == 0, host-checked).
-              // The per-lane path below makes every lane store its own pixel's 128 bytes: a warp-wide float4 store is
-              // 32 separate 16-byte pieces 4*cout bytes apart -- 32 half-used sectors per instruction, which is what
-              // bounds the small-K launches (1x1 convs on the concat: 44 TFLOP/s).  Here the
-              // 32 x 32 block is transposed across the warp first: lane l then holds channel cb + l of all 32 pixels, and
-              // one store instruction writes ONE pixel's 32 channels = a whole 128-byte line (bias / ReLU / residual /
-              // tanh applied in that layout, the residual read becomes coalesced too).
-              lane_transpose32(v, lane);
-              const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-              const float bch = p.bias ? __ldg(p.bias + cb + lane) : 0.f;
-              const unsigned lo = (unsigned)(pix & 0xffffffffu), hi = (unsigned)(pix >> 32);
-#pragma unroll
-              for (int r = 0; r < 32; r++) {
-                const size_t pr = ((size_t)__shfl_sync(0xffffffffu, hi, r) << 32) | (size_t)__shfl_sync(0xffffffffu, lo, r);
-                if (!((vmask >> r) & 1u)) continue;
-                float x = v[r] + bch;
-                if (p.relu) x = fmaxf(x, 0.f);
-                const size_t o = pr * p.cout + cb + lane;
-                if (p.resid) x += p.resid[o];
-                if (p.tanh_out) x = tanhf(x);
-                p.out_f32[o] = x;
-              }
-              continue;
-            }
-          }
           if (valid) {
             if (p.bias) {
 #pragma unroll
@@ -574,23 +530,20 @@ static int make_act_map(CUtensorMap* tm, const gdn_act& a, int stride, const uin
   return encode_tmap_bf16(tm, a.ptr, 5, dims, str, box);
 }
 
-template <int BN, int CG, bool EPI_T = false>
+template <int BN, int CG>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvK& k, size_t smem,
                   cudaStream_t st) {
-  if constexpr (!EPI_T && BN >= 32) {
-    if (k.epi_t) return launch<BN, CG, true>(a0, a1, b, k, smem, st);     // GDN_EPI_T=1 experiment (see gdn_conv2d)
-  }
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, CG, EPI_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     configured[dev] = true;
   }
   const int slots = device_sm_count() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int units = k.total_tiles < slots ? k.total_tiles : slots;
   if (CG == 1) {
-    conv_igemm_kernel<BN, CG, EPI_T><<<units, kThreads, smem, st>>>(a0, a1, b, k);
+    conv_igemm_kernel<BN, CG><<<units, kThreads, smem, st>>>(a0, a1, b, k);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(units * CG);
@@ -604,7 +557,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    GDN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CG, EPI_T>, a0, a1, b, k));
+    GDN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CG>, a0, a1, b, k));
   }
   GDN_LAUNCH_CHECK("conv_igemm_kernel");
   return GDN_OK;
@@ -672,14 +625,6 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   k.cout_pad = d->cout_pad;
   k.stat_sum = d->stat_sum;
   k.stat_sq = d->stat_sqsum;
-  {
-    // GDN_EPI_T=1: transposed (coalesced) fp32 epilogue for launches that write ONLY the fp32 stream -- the
-    // input-gradient convolutions.  EXPERIMENT, off by default: written at the end of round 1 after the GPU budget was
-    // spent; the lane arithmetic is checked on the host (tests/host/epi_sim.cu), the kernel path is not yet run.
-    static int epi = -1;
-    if (epi < 0) { const char* e = getenv("GDN_EPI_T"); epi = (e && atoi(e) == 1) ? 1 : 0; }
-    k.epi_t = (epi == 1 && d->out_f32 && !d->out_bf16.ptr && !d->stat_sum && d->cout == d->cout_pad && d->cout % 32 == 0) ? 1 : 0;
-  }
   if (d->out_bf16.ptr && (d->out_bf16.h != d->dst_h || d->out_bf16.w != d->dst_w || d->out_bf16.c != d->cout))
     return fail(GDN_INVALID_DESC, "gdn_conv2d: out_bf16 extent %dx%dx%d != dst %dx%dx%d", d->out_bf16.h, d->out_bf16.w,
                 d->out_bf16.c, d->dst_h, d->dst_w, d->cout);

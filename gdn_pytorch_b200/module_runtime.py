@@ -37,7 +37,21 @@ def _check_norm(module):
                                   "trains the InstanceNorm branch")
 
 
+def _refuse_replica(module):
+    """nn.DataParallel over several GPUs calls forward on replicas made by _replicate_for_data_parallel: their
+    _parameters are empty (state_dict() holds buffers only), the parameters are non-leaf broadcast views, and the
+    shallow __dict__ copy shares this runtime's engine cache between devices.  That path is what the fused,
+    one-process-per-GPU steps replace (GDN_main.py:153-198 -> trainer.py here); refuse it loudly."""
+    if getattr(module, "_is_replica", False):
+        raise RuntimeError("gdn_b200: this module is an nn.DataParallel replica (several GPUs visible to one process). "
+                           "Multi-GPU runs use one process per GPU: launch with torchrun and use "
+                           "gdn_pytorch_b200.trainer.RtoDTrainStep / DtoDTrainStep (INTEGRATION.md section 3), or wrap as "
+                           "nn.DataParallel(model, device_ids=[local_rank]) to keep the reference's checkpoint keys on one "
+                           "device per process")
+
+
 def _engines(module):
+    _refuse_replica(module)
     d = module.__dict__.get("_gdn_engines")
     if d is None:
         d = {}
@@ -118,6 +132,7 @@ class _NetFn(torch.autograd.Function):
 
 
 def run_network(module, x, istrain):
+    _refuse_replica(module)
     _require_cuda(x)
     graph = module.__dict__.get("_gdn_graph")
     if graph is None:
@@ -206,6 +221,7 @@ class _BlockFn(torch.autograd.Function):
 
 
 def run_block(block, x):
+    _refuse_replica(block)
     _require_cuda(x)
     graph = block.__dict__.get("_gdn_graph")
     if graph is None:

@@ -60,6 +60,19 @@ def test_product_refuses_cpu_tensors():
         ops.compute_errors(torch.zeros(1, 1, 32, 64), torch.zeros(1, 1, 32, 64), torch.zeros(1, 1, 32, 64))
 
 
+def test_dataparallel_replicas_are_refused_with_a_pointer_to_the_fused_steps():
+    """nn.DataParallel over several GPUs forwards on replicas whose _parameters are empty: refused, not mis-served"""
+    from tests.util import build_module
+    m = build_module("AutoEncoder_DtoD", init_weights=False)
+    rep = m._replicate_for_data_parallel()
+    assert rep._is_replica and len(rep._parameters) == 0
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        rep(torch.zeros(1, 1, 32, 64))
+    blk = m.res64_down1._replicate_for_data_parallel()
+    with pytest.raises(RuntimeError, match="DataParallel replica"):
+        blk(torch.zeros(1, 64, 32, 64))
+
+
 def test_bucket_plan_orders_by_readiness():
     from gdn_pytorch_b200.trainer import GradBuckets
     slots = [("a", 0, 1000), ("b", 1000, 3000), ("c", 4000, 500), ("d", 4500, 6000)]

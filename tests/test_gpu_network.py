@@ -434,3 +434,38 @@ def test_device_validator_matches_the_reference_loop():
         assert abs(a - b) <= 5e-3 * abs(b) + 1e-9
     for a, b in zip(mins, want):
         assert abs(a - b) <= 5e-3 * abs(b) + 1e-9
+
+
+def test_eval_after_graph_replayed_steps_uses_the_current_weights():
+    """once the step is a replayed CUDA graph, Adam and the BatchNorm finalize kernels rewrite
+    parameters / running statistics through raw pointers; a cached eval-mode engine (validation every N iterations,
+    trainer.py:17-87) must still re-pack and re-fold.  eval -> 5 steps (2 eager + capture + replays) -> eval must equal
+    a FRESH module loaded from the current state_dict, and differ from the first evaluation."""
+    from gdn_pytorch_b200.trainer import DtoDTrainStep
+    from gdn_pytorch_b200.validate import DeviceValidator
+    from oracle import synth
+    m, _ = _module("AutoEncoder_DtoD", seed=3)
+    dep = synth.synth_depth(B, H, W, 0).to(dev)
+    spa = synth.synth_sparse(dep.cpu(), 0).to(dev)
+    val = DeviceValidator(m, mode="DtoD", dataset="KITTI")
+    m.eval()
+    with torch.no_grad():
+        before = m(dep, istrain=False).clone()
+    val.update(dep, dep, spa)
+    m.train()
+    st = DtoDTrainStep(m, lr=1e-3)          # large steps: stale weights would be unmistakable
+    for _ in range(5):
+        st.step(dep, spa)
+    assert st._graph is not None            # the last steps were replays
+    m.eval()
+    with torch.no_grad():
+        after = m(dep, istrain=False).clone()
+        after_val = val.update(dep, dep, spa).clone()
+    fresh, _ = _module("AutoEncoder_DtoD", seed=99)
+    fresh.load_state_dict({k: v.detach().clone() for k, v in m.state_dict().items()})
+    fresh.eval()
+    with torch.no_grad():
+        want = fresh(dep, istrain=False)
+    assert not torch.equal(after, before)
+    assert torch.equal(after, want) and torch.equal(after_val, want)
+    assert int(m.state_dict()["res64_down1.main.1.num_batches_tracked"]) == 5

@@ -145,13 +145,13 @@ def test_abi_emulator_agrees_with_the_kernels(gname, train):
         assert cos >= 0.97 and _l2(a, b) <= 0.25, (cos, _l2(a, b))
 
 
-@pytest.mark.skipif(os.environ.get("GDN_EPI_T") != "1", reason="experiment: run with GDN_EPI_T=1 (transposed fp32 epilogue)")
 @pytest.mark.parametrize("cin,cout,k,stride2dst,resid,algo", [(64, 64, 1, False, False, 0), (128, 64, 1, False, True, 0),
                                                              (64, 128, 3, False, True, 2), (256, 256, 3, True, False, 1),
                                                              (64, 64, 9, False, True, 2 | (4 << 8) | (1 << 24))])
-def test_transposed_fp32_epilogue_on_hardware(cin, cout, k, stride2dst, resid, algo):
-    """fp32-only outputs (what the input-gradient launches write): with GDN_EPI_T=1 the library routes them to
-    conv_igemm_kernel<.., EPI_T = true>; results must equal the fp64 reference like the default epilogue's"""
+def test_fp32_only_epilogue_strided_destination(cin, cout, k, stride2dst, resid, algo):
+    """fp32-only outputs with residual accumulation and strided destinations (what the input-gradient launches write)
+    against an fp64 reference.  (A warp-transposed, line-per-pixel variant of this epilogue was measured on the B200 in
+    round 2 -- 454 img/s against 550 for the whole step, profiles/r02a_* -- and removed.)"""
     import torch.nn.functional as F
     from gdn_pytorch_b200 import _lib
     g = torch.Generator().manual_seed(cin + cout + k)

@@ -108,37 +108,3 @@ def test_pack_v2_host_simulation_matches_the_layout(case, kind):
                           C.c_void_p(out.data_ptr()), 96)
     assert tb in (16, 32, 64), tb
     assert torch.equal(out, full.to(torch.bfloat16))
-
-
-@pytest.mark.parametrize("bias,relu,resid,tanh_out", [(0, 0, 0, 0), (1, 1, 1, 0), (0, 0, 1, 0), (1, 0, 0, 1)])
-def test_transposed_fp32_epilogue_warp_simulation(bias, relu, resid, tanh_out):
-    """GDN_EPI_T experiment (conv_igemm_kernel<.., EPI_T = true>): the 32 x 32 butterfly transpose + one-line-per-pixel
-    stores write every (pixel, channel) of the valid rows exactly once, with the epilogue operators applied"""
-    lib = _build("epi_sim")
-    g = torch.Generator().manual_seed(4 + bias + 2 * relu)
-    cout, cb, npix = 128, 64, 100
-    acc = torch.randn((32, 32), generator=g)
-    pix = torch.randperm(npix, generator=g)[:32].to(torch.int64).contiguous()     # scattered destination pixels
-    valid = (torch.rand(32, generator=g) > 0.2).to(torch.int32).contiguous()
-    b = torch.randn(cout, generator=g) if bias else None
-    r = torch.randn((npix, cout), generator=g) if resid else None
-    out = torch.full((npix, cout), 777.0)
-    rc = lib.epi_t_host(C.c_void_p(acc.data_ptr()), C.c_void_p(pix.data_ptr()), C.c_void_p(valid.data_ptr()), cout, cb,
-                        C.c_void_p(b.data_ptr() if b is not None else None), relu,
-                        C.c_void_p(r.data_ptr() if r is not None else None), tanh_out, C.c_void_p(out.data_ptr()))
-    assert rc == 0
-    want = torch.full((npix, cout), 777.0)
-    for l in range(32):
-        if not valid[l]:
-            continue
-        x = acc[l].clone()
-        if b is not None:
-            x = x + b[cb:cb + 32]
-        if relu:
-            x = torch.relu(x)
-        if r is not None:
-            x = x + r[pix[l], cb:cb + 32]
-        if tanh_out:
-            x = torch.tanh(x)
-        want[pix[l], cb:cb + 32] = x
-    assert torch.allclose(out, want, rtol=1e-6, atol=1e-6)
