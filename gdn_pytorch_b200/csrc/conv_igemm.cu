@@ -80,6 +80,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  // saturate instead of overflowing to inf: a pre-BatchNorm value beyond +-65504 (possible with loaded checkpoints or
+  // huge fan-in) must stay finite through the normalisation that follows (the reference keeps it in fp32)
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
   __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
@@ -462,7 +466,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < CW; i++)
                       if (cb + i < p.cout) {
-                        if (p.ob_half) reinterpret_cast<__half*>(op)[i] = __float2half_rn(v[i]);
+                        if (p.ob_half) reinterpret_cast<__half*>(op)[i] = __float2half_rn(fminf(fmaxf(v[i], -65504.f), 65504.f));
                         else op[i] = __float2bfloat16(v[i]);
                       }
                   }

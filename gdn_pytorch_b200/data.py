@@ -16,7 +16,8 @@ from . import _lib
 
 def preprocess_u8(src, flip=None, crop=None, out=None):
     """src: uint8 CUDA tensor (N, H, W, C) or (N, H, W); flip: int32 CUDA (N,) or None; crop: float32 CUDA (N, 4) =
-    (scaled_h, scaled_w, off_y, off_x) or None.  Returns fp32 (N, C, H, W) in [-1, 1]."""
+    (scaled_h, scaled_w, off_y, off_x) or None (the zoom is the reference's imresize on the float32 image: per-image
+    min-max byte scaling + PIL's 8-bit bilinear resize, bit-exact).  Returns fp32 (N, C, H, W) in [-1, 1]."""
     if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.uint8):
         raise RuntimeError("gdn_b200.preprocess_u8: src must be a CUDA uint8 tensor (no CPU fallback)")
     if src.dim() == 3:
@@ -30,10 +31,12 @@ def preprocess_u8(src, flip=None, crop=None, out=None):
     if crop is not None:
         crop = crop.to(device=src.device, dtype=torch.float32).contiguous()
     L = _lib.lib()
+    scratch = torch.empty(2 * N, dtype=torch.int32, device=src.device) if crop is not None else None
     with torch.cuda.device(src.device):
         rc = L.gdn_preprocess_u8(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), N, H, W, Cc,
                                  C.c_void_p(flip.data_ptr() if flip is not None else None),
-                                 C.c_void_p(crop.data_ptr() if crop is not None else None), _lib.stream_ptr())
+                                 C.c_void_p(crop.data_ptr() if crop is not None else None),
+                                 C.c_void_p(scratch.data_ptr() if scratch is not None else None), _lib.stream_ptr())
     _lib.check(rc, "preprocess_u8")
     return out
 

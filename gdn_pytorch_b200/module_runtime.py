@@ -106,9 +106,11 @@ class _NetFn(torch.autograd.Function):
         ctx.eng, ctx.fwd_id, ctx.names = eng, eng._fwd_id, names
         depth = eng.depth().clone()
         ctx.save_for_backward(depth)
+        ctx.set_materialize_grads(False)
         if istrain:
+            # the feature maps stay differentiable outputs so that a loss on them is REFUSED in backward() instead of
+            # silently contributing nothing (the reference would back-propagate it)
             feats = [eng.value_nchw(n).clone() for n in graph.outputs[:-1]]
-            ctx.mark_non_differentiable(*feats)
             return (*feats, depth)
         return depth
 
@@ -119,6 +121,10 @@ class _NetFn(torch.autograd.Function):
             raise RuntimeError("gdn_b200: backward() called after another forward of the same module and shape; the "
                                "engine keeps one set of activations (call backward before the next forward)")
         (depth,) = ctx.saved_tensors
+        if any(g is not None for g in grads[:-1]):
+            raise NotImplementedError("gdn_b200: gradients through the feature maps returned by forward(x, istrain=True) are "
+                                      "not implemented in the module API (the reference never back-propagates through them; "
+                                      "RtoDTrainStep(guidance_grad=True) is the supported guidance-gradient path)")
         dout = grads[-1]
         if dout is None:
             dout = torch.zeros_like(depth)
@@ -146,7 +152,18 @@ def run_network(module, x, istrain):
         raise ValueError("gdn_b200: height and width must be multiples of 16 (got %dx%d), like the reference networks "
                          "themselves (SURVEY.md 0.4: odd sizes break the skip concatenation)" % (x.shape[2], x.shape[3]))
     named = [(n, p) for n, p in module.named_parameters()]
-    needs_grad = module.training and torch.is_grad_enabled() and any(p.requires_grad for _, p in named)
+    wants_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in named)
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError("gdn_b200: input gradients through the module API are not implemented (nothing on the "
+                                  "reference path needs d/d input); RtoDTrainStep(guidance_grad=True) back-propagates "
+                                  "through the frozen DtoD encoder")
+    if wants_grad and not module.training and not module.__dict__.get("_gdn_warned_eval_grad"):
+        import warnings
+        module.__dict__["_gdn_warned_eval_grad"] = True
+        warnings.warn("gdn_b200: eval-mode forward with autograd enabled returns a tensor WITHOUT grad_fn (the eval engine "
+                      "folds BatchNorm and keeps no activations); wrap evaluation in torch.no_grad() like the reference's "
+                      "validate(), or call model.train() to get gradients", RuntimeWarning, stacklevel=3)
+    needs_grad = module.training and wants_grad
     if needs_grad:
         names = tuple(n for n, _ in named)
         return _NetFn.apply(x, module, graph, bool(istrain is True), names, *[p for _, p in named])

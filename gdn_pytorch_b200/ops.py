@@ -200,6 +200,11 @@ class FusedAdam(torch.optim.Optimizer):
         if self.dyn is not None:
             self.dyn[0:1].fill_(lr)
 
+    def set_hyper(self, betas, eps, weight_decay):
+        """betas / eps / weight decay are passed by value at launch: valid until the step is captured in a CUDA graph"""
+        for g in self.param_groups:
+            g["betas"], g["eps"], g["weight_decay"] = tuple(betas), eps, weight_decay
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None

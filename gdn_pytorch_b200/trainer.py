@@ -267,6 +267,18 @@ class _StepBase:
     def load_state_dict(self, sd):
         """inverse of state_dict(); parameters are copied IN PLACE (the flat buffer and every raw pointer the
         engines hold stay valid), the CUDA graph keeps replaying with the restored step count / learning rate"""
+        hy = sd.get("hyper")
+        if hy is not None:
+            saved = (tuple(float(b) for b in hy["betas"]), float(hy["eps"]), float(hy["weight_decay"]))
+            mine = (tuple(float(b) for b in self.hyper[0]), float(self.hyper[1]), float(self.hyper[2]))
+            if saved != mine:
+                if self._graph is not None:
+                    raise RuntimeError("gdn_b200: checkpoint Adam hyper-parameters %s differ from this step's %s and the step "
+                                       "is already captured in a CUDA graph; construct the step with the saved values"
+                                       % (saved, mine))
+                self.hyper = (saved[0], saved[1], saved[2])     # resume exactly: the checkpoint's betas / eps / decay win
+                if self.opt is not None:
+                    self.opt.set_hyper(*self.hyper)
         self.model.load_state_dict(sd["model"])
         self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1   # engines re-pack / re-fold
         if self.eng is not None:

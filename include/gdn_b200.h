@@ -207,11 +207,14 @@ int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int 
 /* ---- device-side input pipeline (the reference's per-sample CPU transforms) ----------------
  * src: uint8 [n][h][w][c] (HWC, as decoded); dst: fp32 [n][c][h][w] in [-1, 1] = Normalize(0.5, 0.5)(ArrayToTensor(.)),
  * transform_list.py:84-113.  flip[n] != 0 mirrors sample n horizontally (RandomHorizontalFlip, :161-169); crop[n] =
- * (scaled_h, scaled_w, off_y, off_x) zooms sample n to scaled_h x scaled_w (bilinear, rounded to uint8) and keeps
- * the h x w window at the offset (RandomScaleCrop, :189-203).  Both may be NULL.  The random draws stay on the host
- * (gdn_pytorch_b200/data.py replays the reference's RNG calls). */
+ * (scaled_h, scaled_w, off_y, off_x) zooms sample n to scaled_h x scaled_w (scaled >= h, w) and keeps the h x w window
+ * at the offset (RandomScaleCrop, :189-203).  The zoom is scipy.misc.imresize on the loader's float32 image: per-image
+ * min-max byte scaling of the whole array + PIL's two-pass 8-bit BILINEAR resize, bit-exact (the arithmetic of
+ * gdn_bytescale / gdn_resize_u8 below).  Both may be NULL.  scratch: 8*n bytes of device memory (per-image min / max),
+ * required when crop != NULL.  The random draws stay on the host (gdn_pytorch_b200/data.py replays the reference's RNG
+ * calls). */
 int gdn_preprocess_u8(const uint8_t* src, float* dst, int n, int h, int w, int c, const int32_t* flip, const float* crop,
-                      gdn_stream stream);
+                      void* scratch, gdn_stream stream);
 
 /* ---- demo path: the image resizing of src/depth_extract.py:23-58,86,138 ------------------------
  * scipy.misc.imresize(arr, size, 'bilinear') = bytescale + PIL BILINEAR resize of the 8-bit image, bit-exact.

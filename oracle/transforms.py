@@ -2,13 +2,14 @@
 
 Reference: /root/reference/src/transform_list.py -- ArrayToTensor (:95-113) + Normalize (:84-93) verbatim arithmetic
 (float / 255, then sub_(0.5).div_(0.5)); RandomHorizontalFlip (:161-169) = np.fliplr; RandomScaleCrop (:189-203) =
-imresize to (scaled_h, scaled_w) + crop.  scipy.misc.imresize (PIL bilinear, uint8 result) no longer exists in SciPy
-(SURVEY.md Appendix C), so the zoom is restated as pixel-centre-aligned bilinear interpolation rounded to uint8 --
-parity for that step is therefore "unpinned" against the reference and held to +-1 grey level.
+``imresize(im, (scaled_h, scaled_w))`` + crop.  The loader hands the transforms FLOAT32 arrays
+(src/datasets/datasets_list.py:81-86 load_as_float = imread(..).astype(np.float32)), so scipy.misc.imresize first
+byte-scales every image (per-image min-max stretch of the whole array to 0..255) and then resizes the 8-bit image with
+PIL: that is oracle/imresize.py (resize pinned bit-for-bit on Pillow; bytescale restated from the published SciPy 1.2
+source, unpinned -- scipy.misc no longer exists).
 """
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 
 def to_tensor_normalize(img_u8):
@@ -30,10 +31,12 @@ def flip_scale_crop(img_u8, flip, crop):
     if flip:
         im = np.copy(np.fliplr(im))                                                     # :166
     if crop is not None:
+        from .imresize import imresize
         sh, sw, oy, ox = (int(v) for v in crop)
-        h, w = im.shape[0], im.shape[1]
-        t = torch.from_numpy(np.ascontiguousarray(im.transpose(2, 0, 1))).float()[None]
-        z = F.interpolate(t, size=(sh, sw), mode="bilinear", align_corners=False)[0]
-        z = z.round().clamp(0, 255).byte().numpy().transpose(1, 2, 0)
+        h, w, c = im.shape
+        arr = im.astype(np.float32)                                                     # load_as_float
+        z = imresize(arr[:, :, 0] if c == 1 else arr, (sh, sw))                         # :197 (2-D 'L' / HxWx3 'RGB')
+        if z.ndim == 2:
+            z = z[:, :, None]
         im = z[oy:oy + h, ox:ox + w]                                                    # :201
     return im

@@ -29,20 +29,28 @@ def test_to_tensor_normalize_and_flip_are_bit_exact(n, h, w, c):
     assert float(got2.min()) >= -1.0 and float(got2.max()) <= 1.0
 
 
-def test_scale_crop_matches_restated_zoom():
-    """RandomScaleCrop: +-1 grey level (rounding ties of the interpolation), identical elsewhere"""
+@pytest.mark.parametrize("c,lo,hi", [(3, 0, 256), (3, 17, 201), (0, 40, 130), (1, 0, 256), (0, 7, 8)])
+def test_scale_crop_is_the_reference_imresize_bit_for_bit(c, lo, hi):
+    """RandomScaleCrop (transform_list.py:189-203) on the loader's float32 images: scipy.misc.imresize = per-image min-max
+    byte scaling + PIL's 8-bit BILINEAR resize, then the crop -- identical bytes, hence identical fp32 tensors.  Images
+    whose range is not exactly [0, 255] (depth PNGs) exercise the stretch; a constant image the max == min case."""
     from gdn_pytorch_b200.data import preprocess_u8, DeviceInputPipeline
     from oracle import transforms as OT
     n, h, w = 6, 64, 96
-    x = _batch(n, h, w, 3, 5)
+    rs = np.random.RandomState(5 + c + lo)
+    x = rs.randint(lo, hi, size=(n, h, w, c) if c else (n, h, w)).astype(np.uint8)
     pipe = DeviceInputPipeline(dev, train=True, seed=1)
     flip, crop = pipe.draw(n, h, w)
+    crop[0] = (h, w, 0, 0)                       # both passes skipped
+    crop[1] = (h, crop[1][1], 0, crop[1][3])     # horizontal pass only
+    crop[2] = (crop[2][0], w, crop[2][2], 0)     # vertical pass only
     assert ((crop[:, 0] >= h) & (crop[:, 0] <= int(h * 1.15)) & (crop[:, 2] >= 0) & (crop[:, 2] <= crop[:, 0] - h)).all()
     got = preprocess_u8(torch.from_numpy(x).to(dev), torch.from_numpy(flip).to(dev), torch.from_numpy(crop).to(dev)).cpu()
     want = torch.stack([OT.to_tensor_normalize(OT.flip_scale_crop(x[i], flip[i], crop[i])) for i in range(n)])
-    d = (got - want).abs()
-    assert d.max().item() <= 2.0 / 255 + 1e-6                 # one grey level in [-1, 1] units
-    assert (d > 1e-6).float().mean().item() < 0.02            # ... and only at rounding ties
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+    if hi - lo > 1 and (lo, hi) != (0, 256):     # the stretch is visible: the zoomed image spans the full byte range
+        assert float(got.max()) > 0.9 and float(got.min()) < -0.9
 
 
 def test_pipeline_yields_what_the_training_step_consumes():
