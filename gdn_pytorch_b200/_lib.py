@@ -27,6 +27,7 @@ class ConvDesc(C.Structure):
         ("dst_h", C.c_int32), ("dst_w", C.c_int32), ("dst_sy", C.c_int32), ("dst_sx", C.c_int32),
         ("dst_oy", C.c_int32), ("dst_ox", C.c_int32),
         ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("out16_is_half", C.c_int32),
+        ("bwd_raw", C.c_void_p), ("bwd_coef", C.c_void_p), ("bwd_relu", C.c_int32),
     ]
 
 

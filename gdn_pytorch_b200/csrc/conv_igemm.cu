@@ -62,6 +62,11 @@ struct ConvK {
   int cout, cout_pad;
   double* stat_sum;
   double* stat_sq;
+  // fused BatchNorm-backward statistics (input-gradient launches that write the LAST contribution to a tensor's gradient):
+  // the unit that produced the tensor: its stored pre-BN output and per-channel (scale, shift, mean, rstd)
+  const __half* bs_raw;      // fp16 [n][dst_h][dst_w][cout], NULL = off
+  const float4* bs_coef;     // [cout]
+  int bs_relu;
 };
 
 struct Ring {
@@ -347,7 +352,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     Ring rc;
     const int q = warp;
     const int m = q * 32 + lane;
-    const bool do_stats = p.stat_sum != nullptr;
+    const bool do_bstats = p.bs_raw != nullptr;                  // sum g, sum g*xhat of the masked total gradient
+    const bool do_stats = p.stat_sum != nullptr && !do_bstats;   // forward: sum x, sum x^2 of the raw accumulators
+    const bool any_stats = p.stat_sum != nullptr;
     for (int t = cta_first; t < p.total_tiles; t += cta_step) {
       int nblk, tx, ty, img;
       decode(t, nblk, tx, ty, img);
@@ -410,6 +417,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               atomicAdd(&s_stat[1][cc + lane], t2);
             }
           }
+          const bool full = (cb + CW <= p.cout);
           if (valid) {
             if (p.bias) {
 #pragma unroll
@@ -420,7 +428,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
               for (int i = 0; i < CW; i++) v[i] = fmaxf(v[i], 0.f);
             }
-            const bool full = (cb + CW <= p.cout);
             if (p.resid) {
               const float* rp = p.resid + pix * p.cout + cb;
               if (full) {
@@ -435,6 +442,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   if (cb + i < p.cout) v[i] += rp[i];
               }
             }
+          }
+          if constexpr (CW == 32) {
+            if (do_bstats) {
+              // v is now the TOTAL gradient of the destination tensor (this launch is its last contribution: host
+              // contract).  Apply the ReLU mask of the unit that produced the tensor and reduce, per channel, sum g and
+              // sum g*xhat -- what gdn_bn_bwd_reduce would compute in a separate pass over the fp32 gradient -- with the
+              // same expressions (mask: fma(x, scale, shift) <= 0; xhat = (x - mean)*rstd).
+              float s2[CW];
+              if (valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.bs_raw + pix * p.cout + cb);
+#pragma unroll
+                for (int q4 = 0; q4 < CW / 8; q4++) {
+                  const uint4 u = __ldg(rp + q4);
+                  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int h2 = 0; h2 < 4; h2++) {
+                    const float2 xy = __half22float2(*reinterpret_cast<const __half2*>(&w4[h2]));
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                      const int i = q4 * 8 + h2 * 2 + e;
+                      const float x = e ? xy.y : xy.x;
+                      const float4 cf = __ldg(p.bs_coef + cb + i);
+                      if (p.bs_relu && fmaf(x, cf.x, cf.y) <= 0.f) v[i] = 0.f;
+                      s2[i] = v[i] * ((x - cf.z) * cf.w);
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < CW; i++) s2[i] = 0.f;
+              }
+              float s1[CW];
+#pragma unroll
+              for (int i = 0; i < CW; i++) s1[i] = valid ? v[i] : 0.f;
+              const float t1 = lane_transpose_sum<CW>(s1, lane);
+              const float t2 = lane_transpose_sum<CW>(s2, lane);
+              atomicAdd(&s_stat[0][cc + lane], t1);
+              atomicAdd(&s_stat[1][cc + lane], t2);
+            }
+          }
+          if (valid) {
             if (p.tanh_out) {
 #pragma unroll
               for (int i = 0; i < CW; i++) v[i] = tanhf(v[i]);
@@ -481,7 +529,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (CG == 2) mbar_arrive_leader(&acc_empty[rc.i]); else mbar_arrive(&acc_empty[rc.i]);
       }
       rc.next(p.acc_bufs);
-      if (do_stats && p.cout_blocks > 1) {
+      if (any_stats && p.cout_blocks > 1) {
         // the channel block changes from tile to tile: flush the per-CTA partials now (4 epilogue warps only)
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int i = threadIdx.x; i < BN; i += 128) {
@@ -493,7 +541,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
-    if (do_stats && p.cout_blocks == 1) {
+    if (any_stats && p.cout_blocks == 1) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int i = threadIdx.x; i < BN; i += 128) {
         if (i < p.cout) {
@@ -629,6 +677,16 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   k.cout_pad = d->cout_pad;
   k.stat_sum = d->stat_sum;
   k.stat_sq = d->stat_sqsum;
+  k.bs_raw = reinterpret_cast<const __half*>(d->bwd_raw);
+  k.bs_coef = reinterpret_cast<const float4*>(d->bwd_coef);
+  k.bs_relu = d->bwd_relu;
+  if (d->bwd_raw) {
+    if (!d->bwd_coef || !d->stat_sum || !d->stat_sqsum)
+      return fail(GDN_INVALID_DESC, "gdn_conv2d: bwd_raw needs bwd_coef and the stat_sum / stat_sqsum accumulators");
+    if (d->cout != d->cout_pad || d->cout % 32 || d->tanh_out || d->out_reflect || d->out16_is_half ||
+        (d->out_bf16.ptr && d->out_bf16.pad))
+      return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: fused BatchNorm-backward statistics need cout %% 32 == 0 and plain outputs");
+  }
   if (d->out_bf16.ptr && (d->out_bf16.h != d->dst_h || d->out_bf16.w != d->dst_w || d->out_bf16.c != d->cout))
     return fail(GDN_INVALID_DESC, "gdn_conv2d: out_bf16 extent %dx%dx%d != dst %dx%dx%d", d->out_bf16.h, d->out_bf16.w,
                 d->out_bf16.c, d->dst_h, d->dst_w, d->cout);

@@ -224,7 +224,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ rstd_out, int C) {
+                                   float* __restrict__ rstd_out, float4* __restrict__ coef4, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double m = sum[c] / count;
@@ -236,6 +236,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   shift[c] = b - (float)m * g * rstd;
   mean_out[c] = (float)m;
   rstd_out[c] = rstd;
+  // what a dgrad epilogue needs per channel for the fused BatchNorm-backward statistics: y = x*scale + shift (ReLU
+  // mask), xhat = (x - mean)*rstd -- the same expressions gdn_bn_bwd_reduce evaluates
+  if (coef4) coef4[c] = make_float4(g * rstd, b - (float)m * g * rstd, (float)m, rstd);
   if (running_mean) {
     const double unb = count > 1 ? var * count / (count - 1) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
@@ -550,7 +553,19 @@ struct BnBwd {
   float* dgamma;                  // += sum_gx   (may be NULL)
   float* dbeta;                   // += sum_g
   int raw_half;
+  int dact_bf16;                  // dact holds bf16 (written by a convolution epilogue with the ReLU mask already applied)
 };
+
+// 8 consecutive gradient values of element offset `off` (fp32 stream, or the bf16 buffer a dgrad epilogue wrote)
+__device__ __forceinline__ void bn_grad8(const BnBwd& b, size_t off, float* d) {
+  if (b.dact_bf16) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(b.dact) + off)), d);
+  } else {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(b.dact + off));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(b.dact + off + 4));
+    d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+  }
+}
 
 
 // Per-channel reductions: threads are (pixel lane, 8-channel group) with the channel group fastest, so a warp
@@ -580,9 +595,8 @@ __global__ void bn_bwd_reduce_kernel(const BnBwd b) {
       float x[8];
       if (b.raw_half) unpack8h(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
       else unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), x);
-      const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
-      const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
-      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float d[8];
+      bn_grad8(b, (size_t)(pix * b.C + c8), d);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         float gq = d[j];
@@ -644,9 +658,8 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
       float xr[8];
       if (b.raw_half) unpack8h(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
       else unpack8(*reinterpret_cast<const uint4*>(b.raw + pix * b.C + c8), xr);
-      const float4 d0 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8);
-      const float4 d1 = *reinterpret_cast<const float4*>(b.dact + pix * b.C + c8 + 4);
-      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float d[8];
+      bn_grad8(b, (size_t)(pix * b.C + c8), d);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         float gq = d[j];
@@ -663,10 +676,8 @@ __global__ void bn_bwd_apply_kernel(const BnBwd b) {
 // ---- fast paths: contiguous pixel ranges per CTA, 32-bit index math, two items in flight per thread
 __device__ __forceinline__ void bn_load8(const BnBwd& b, size_t off, float* x, float* d) {
   const uint4 q = __ldg(reinterpret_cast<const uint4*>(b.raw + off));
-  const float4 d0 = __ldg(reinterpret_cast<const float4*>(b.dact + off));
-  const float4 d1 = __ldg(reinterpret_cast<const float4*>(b.dact + off + 4));
+  bn_grad8(b, off, d);
   if (b.raw_half) unpack8h(q, x); else unpack8(q, x);
-  d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
 }
 
 // per-channel sums of g and g*(x - mean) (scaled by rstd at the end); items = npix * cg, block-contiguous chunks
@@ -809,8 +820,7 @@ __global__ void fold_grad_kernel(const FoldK f) {
         const float w = wys[a] * wxs[b];
         for (int p = 0; p < cy; p++)
           for (int q = 0; q < cx; q++) {
-            const float4 v = *reinterpret_cast<const float4*>(
-                f.dpad + (((long long)n * Hq + my[p]) * Wq + mx[q]) * f.ctot + f.c_off + c4);
+            const FoldV4 v = fold_load4(f, (size_t)((((long long)n * Hq + my[p]) * Wq + mx[q]) * f.ctot + f.c_off + c4));
             acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
           }
       }
@@ -825,100 +835,11 @@ __global__ void fold_grad_kernel(const FoldK f) {
 }
 
 
-// fast path: one source row (n, y) per CTA iteration; the hi-res rows feeding it (and their reflection images) are
-// found once per row (shared memory), the columns per thread in registers (fully unrolled candidate x mirror grid),
-// 32-bit index math, 4 channels (16 B) per thread item.
-__global__ void __launch_bounds__(kEwThreads) fold_rows_kernel(const FoldK f, const int lg_cg, const int rows) {
-  __shared__ int s_prow[12];
-  __shared__ float s_pw[12];
-  __shared__ int s_np;
-  const int cgm = (1 << lg_cg) - 1;
-  const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
-  const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
-  const int items = f.W << lg_cg;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / f.H, y = row - n * f.H;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int np = 0;
-      const int ylo = f.up ? 2 * y - 1 : (f.dilate ? 2 * y : y), yhi = f.up ? 2 * y + 2 : ylo;
-      for (int Y = ylo; Y <= yhi; Y++) {
-        if (Y < 0 || Y >= OH) continue;
-        float w = 1.f;
-        if (f.up) {
-          int a0, a1;
-          float w1;
-          up_coord(Y, f.H, f.up, a0, a1, w1);
-          w = (a0 == y ? 1.f - w1 : 0.f) + (a1 == y ? w1 : 0.f);
-          if (w == 0.f) continue;
-        }
-        int my[3];
-        const int cy = mirror_set(Y, OH, f.P, f.reflect, my);
-        for (int p = 0; p < cy; p++) { s_prow[np] = my[p]; s_pw[np++] = w; }
-      }
-      s_np = np;
-    }
-    __syncthreads();
-    const int np = s_np;
-    const size_t img = (size_t)n * Hq;
-    for (int it = threadIdx.x; it < items; it += kEwThreads) {
-      const int x = it >> lg_cg, c4 = (it & cgm) * 4;
-      // candidate hi-res columns (4 when upsampling, else 1) x up to 3 reflection images; -1 = unused
-      int pcol[4][3];
-      float qw[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        qw[k] = 0.f;
-        pcol[k][0] = pcol[k][1] = pcol[k][2] = -1;
-        int X;
-        if (f.up) X = 2 * x - 1 + k;
-        else if (k == 0) X = f.dilate ? 2 * x : x;
-        else continue;
-        if (X < 0 || X >= OW) continue;
-        float w = 1.f;
-        if (f.up) {
-          int a0, a1;
-          float w1;
-          up_coord(X, f.W, f.up, a0, a1, w1);
-          w = (a0 == x ? 1.f - w1 : 0.f) + (a1 == x ? w1 : 0.f);
-          if (w == 0.f) continue;
-        }
-        qw[k] = w;
-        pcol[k][0] = X + f.P;
-        if (f.reflect) {
-          if (X >= 1 && X <= f.P) pcol[k][1] = f.P - X;
-          if (X >= OW - 1 - f.P && X <= OW - 2) pcol[k][2] = f.P + 2 * (OW - 1) - X;
-        }
-      }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < np; p++) {
-        const float* rowp = f.dpad + ((img + s_prow[p]) * Wq) * f.ctot + f.c_off + c4;
-        const float wr = s_pw[p];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-          for (int m = 0; m < 3; m++) {
-            if (pcol[k][m] < 0) continue;
-            const float w = wr * qw[k];
-            const float4 v = __ldg(reinterpret_cast<const float4*>(rowp + (size_t)pcol[k][m] * f.ctot));
-            acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
-          }
-        }
-      }
-      float* o = f.dact + ((size_t)row * f.W + x) * f.C + c4;
-      if (f.accumulate) {
-        const float4 v = *reinterpret_cast<const float4*>(o);
-        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-      }
-      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    }
-  }
-}
-
-// second version: the column candidates / weights of every source column are tabulated ONCE per CTA in shared memory
-// (they do not depend on the row or the channel), the per-item loop is loads + FMAs only.  The first version spent
-// its time recomputing them per item (ALU-bound at ~1 TB/s effective on the x2-bilinear adjoints).  Same accumulation
-// order, bit-identical results.  Dynamic shared memory: W * 64 bytes.
+// fast path: one source row (n, y) per CTA iteration.  The column candidates / weights of every source column are
+// tabulated ONCE per CTA in shared memory (they do not depend on the row or the channel), the hi-res rows feeding a
+// source row once per row; the per-item loop is loads + FMAs only (a first version that recomputed the candidates per
+// item was ALU-bound at ~1 TB/s on the x2-bilinear adjoints; same-box A/B in profiles/r02a_*).  Dynamic shared memory:
+// W * 64 bytes.
 __global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
   extern __shared__ __align__(16) unsigned char s_fold[];
   int* s_pc = reinterpret_cast<int*>(s_fold);                                  // [W][12]
@@ -1238,11 +1159,12 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
 
 GDN_API int gdn_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
                             float eps, float momentum, float* running_mean, float* running_var, float* scale,
-                            float* shift, float* mean, float* rstd, int c, gdn_stream stream) {
+                            float* shift, float* mean, float* rstd, float* coef4, int c, gdn_stream stream) {
   if (!sum || !sqsum || !gamma || !beta || !scale || !shift || !mean || !rstd || c < 1)
     return fail(GDN_INVALID_DESC, "gdn_bn_finalize: null pointer");
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, gamma, beta, eps, momentum,
-                                                                     running_mean, running_var, scale, shift, mean, rstd, c);
+                                                                     running_mean, running_var, scale, shift, mean, rstd,
+                                                                     reinterpret_cast<float4*>(coef4), c);
   GDN_LAUNCH_CHECK("bn_finalize_kernel");
   return GDN_OK;
 }
@@ -1303,8 +1225,9 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
 static int fill_bnbwd(const gdn_bn_bwd_desc* d, BnBwd& b) {
   if (!d || !d->dact || !d->raw || !d->scale || !d->shift || !d->mean || !d->rstd || !d->sum_g || !d->sum_gx)
     return fail(GDN_INVALID_DESC, "gdn_bn_bwd: null pointer");
+  if (d->dact_is_bf16 && d->dilate) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_bn_bwd: bf16 gradient input with dilation");
   if (d->c % 8 || d->c > 512 || (256 % (d->c / 8))) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_bn_bwd: channels %d", d->c);
-  b.dact = d->dact;
+  b.dact = reinterpret_cast<const float*>(d->dact);
   b.raw = (const __nv_bfloat16*)d->raw;
   b.scale = d->scale; b.shift = d->shift; b.mean = d->mean; b.rstd = d->rstd;
   b.relu = d->relu;
@@ -1315,6 +1238,7 @@ static int fill_bnbwd(const gdn_bn_bwd_desc* d, BnBwd& b) {
   b.H = d->h; b.W = d->w; b.dilate = d->dilate;
   b.dgamma = d->dgamma; b.dbeta = d->dbeta;
   b.raw_half = d->raw_is_half;
+  b.dact_bf16 = d->dact_is_bf16;
   return GDN_OK;
 }
 
@@ -1380,10 +1304,12 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
   if (d->up > 1) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: only the align_corners=False adjoint is implemented");
   if (d->reflect && (d->pad >= d->h || d->pad >= d->w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: reflection pad too large");
   FoldK f{};
-  f.dpad = d->dpad; f.ctot = d->ctot; f.c_off = d->c_off;
+  f.dpad = reinterpret_cast<const float*>(d->dpad); f.ctot = d->ctot; f.c_off = d->c_off;
   f.N = d->n; f.H = d->h; f.W = d->w; f.C = d->c;
   f.P = d->pad; f.reflect = d->reflect; f.up = d->up; f.dilate = d->dilate;
   f.dact = d->dact; f.accumulate = d->accumulate;
+  f.dpad_bf16 = d->dpad_is_bf16;
+  if (thin && f.dpad_bf16) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: bf16 input needs channel counts that are multiples of 4");
   if (thin) {
     fold_thin_kernel<<<ew_grid((long long)f.N * f.H * f.W * f.C), kEwThreads, 0, (cudaStream_t)stream>>>(f);
     GDN_LAUNCH_CHECK("fold_thin_kernel");
@@ -1394,16 +1320,11 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
     if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
       const int rows = f.N * f.H;
       const size_t smem = (size_t)f.W * (kFoldColInts * sizeof(int) + 4 * sizeof(float));
-      static int v1 = -1;                       // GDN_FOLD_V1=1: the first version of the kernel (A/B knob)
-      if (v1 < 0) { const char* e = getenv("GDN_FOLD_V1"); v1 = (e && atoi(e) == 1) ? 1 : 0; }
-      if (!v1 && smem <= 40 * 1024) {
+      if (smem <= 40 * 1024) {
         fold_rows2_kernel<<<ew_row_grid(rows), kEwThreads, smem, (cudaStream_t)stream>>>(f, lg, rows);
         GDN_LAUNCH_CHECK("fold_rows2_kernel");
         return GDN_OK;
       }
-      fold_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(f, lg, rows);
-      GDN_LAUNCH_CHECK("fold_rows_kernel");
-      return GDN_OK;
     }
   }
   const long long work = (long long)f.N * f.H * f.W * (f.C / 4);

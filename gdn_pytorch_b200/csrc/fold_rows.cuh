@@ -21,13 +21,32 @@
 namespace gdn {
 
 struct FoldK {
-  const float* dpad;   // fp32 [N][OH+2P][OW+2P][ctot]: gradient w.r.t. the conv's input buffer
+  const float* dpad;   // [N][OH+2P][OW+2P][ctot]: gradient w.r.t. the conv's input buffer (fp32, or bf16 when dpad_bf16)
   int ctot, c_off;
   int N, H, W, C;      // source activation extent
   int P, reflect, up, dilate;
   float* dact;         // fp32 [N][H][W][C]
   int accumulate;
+  int dpad_bf16;       // dpad holds bf16 (an input-gradient convolution wrote it through its bf16 output)
 };
+
+struct FoldV4 { float x, y, z, w; };
+
+// four consecutive channels at ELEMENT offset `off` of dpad (bf16 -> fp32 is a 16-bit shift: same code on host and device)
+GDN_HD FoldV4 fold_load4(const FoldK& f, size_t off) {
+  FoldV4 r;
+  if (f.dpad_bf16) {
+    const uint64_t u = *reinterpret_cast<const uint64_t*>(reinterpret_cast<const uint16_t*>(f.dpad) + off);
+    const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+    const uint32_t b0 = lo << 16, b1 = lo & 0xffff0000u, b2 = hi << 16, b3 = hi & 0xffff0000u;
+    r.x = *reinterpret_cast<const float*>(&b0); r.y = *reinterpret_cast<const float*>(&b1);
+    r.z = *reinterpret_cast<const float*>(&b2); r.w = *reinterpret_cast<const float*>(&b3);
+  } else {
+    const float4 v = GDN_LDG4(f.dpad + off);
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+  }
+  return r;
+}
 
 // source coordinates / weight of hi-res index o for x2 bilinear upsampling (mode 1: align_corners=False, 2: True)
 GDN_HD void up_coord(int o, int in, int mode, int& i0, int& i1, float& w1) {
@@ -116,14 +135,14 @@ GDN_HD void fold_item(const FoldK& f, int lg_cg, int Hq, int Wq, int row, int it
   const float* qw = qws + (size_t)x * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = 0; p < np; p++) {
-    const float* rowp = f.dpad + ((img + prow[p]) * Wq) * f.ctot + f.c_off + c4;
+    const size_t rowo = ((img + prow[p]) * Wq) * f.ctot + f.c_off + c4;
     const float wr = pw[p];
     for (int k = 0; k < 4; k++) {
       const float w = wr * qw[k];
       for (int m = 0; m < 3; m++) {
         const int col = pc[3 * k + m];
         if (col < 0) continue;
-        const float4 v = GDN_LDG4(rowp + (size_t)col * f.ctot);
+        const FoldV4 v = fold_load4(f, rowo + (size_t)col * f.ctot);
 #if defined(__CUDA_ARCH__)
         acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
 #else

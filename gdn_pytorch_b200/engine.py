@@ -39,7 +39,8 @@ class BnBwdDesc(C.Structure):
     _fields_ = [("dact", C.c_void_p), ("raw", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("relu", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("c", C.c_int32), ("sum_g", C.c_void_p), ("sum_gx", C.c_void_p), ("dy", C.c_void_p),
-                ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("raw_is_half", C.c_int32)]
+                ("dilate", C.c_int32), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("raw_is_half", C.c_int32),
+                ("dact_is_bf16", C.c_int32)]
 
 
 class FrozenBwdDesc(C.Structure):
@@ -51,7 +52,7 @@ class FrozenBwdDesc(C.Structure):
 class FoldDesc(C.Structure):
     _fields_ = [("dpad", C.c_void_p), ("ctot", C.c_int32), ("c_off", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("c", C.c_int32), ("pad", C.c_int32), ("reflect", C.c_int32), ("up", C.c_int32),
-                ("dilate", C.c_int32), ("dact", C.c_void_p), ("accumulate", C.c_int32)]
+                ("dilate", C.c_int32), ("dact", C.c_void_p), ("accumulate", C.c_int32), ("dpad_is_bf16", C.c_int32)]
 
 
 class PackDesc(C.Structure):
@@ -419,6 +420,7 @@ class Engine:
                 cu.shift = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.mean = torch.empty(u.cout, dtype=torch.float32, device=dev)
                 cu.rstd = torch.empty(u.cout, dtype=torch.float32, device=dev)
+                cu.coef4 = torch.empty((u.cout, 4), dtype=torch.float32, device=dev)   # (scale, shift, mean, rstd) interleaved
                 d.out_bf16 = Act(cu.raw.data_ptr(), N, ho, wo, u.cout, 0)
                 d.out16_is_half = 1
                 d.stat_sum = cu.stat[0].data_ptr()
@@ -435,7 +437,7 @@ class Engine:
                                            C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), C.c_void_p(rm.data_ptr()),
                                            C.c_void_p(rv.data_ptr()), C.c_void_p(cu.scale.data_ptr()),
                                            C.c_void_p(cu.shift.data_ptr()), C.c_void_p(cu.mean.data_ptr()),
-                                           C.c_void_p(cu.rstd.data_ptr()), c, s)
+                                           C.c_void_p(cu.rstd.data_ptr()), C.c_void_p(cu.coef4.data_ptr()), c, s)
                     if rc:
                         _lib.check(rc, "bn_finalize " + u.conv)
                 self.fwd.append(finalize)
@@ -666,7 +668,31 @@ class Engine:
         zero_sums.label = "misc"
         self.bwd.append(zero_sums)
         self.launches_bwd += 1
-        bn_i = 0
+        self._bn_idx = {}
+        for u in self.units:
+            if u.bn is not None:
+                self._bn_idx[u.conv] = len(self._bn_idx)
+        # Fused BatchNorm-backward statistics: the input-gradient convolution that writes the LAST contribution to a
+        # tensor's gradient also reduces sum g / sum g*xhat of the unit that produced the tensor in its epilogue (and
+        # applies that unit's ReLU mask), so the separate reduce pass over the gradient disappears; when nothing else
+        # reads the fp32 gradient it is written as bf16 only (``gm``), which is all the apply pass needs.
+        # last_contrib[t]: the unit whose backward adds the final term to d(t) -- the live consumer / residual user
+        # that comes FIRST in forward order (backward visits units in reverse).
+        self._fuse_bnbwd = os.environ.get("GDN_FUSE_BNBWD", "1") != "0"
+        live = {self.units[-1].out}
+        for u in reversed(self.units):
+            if u.out in live:
+                live.update(u.srcs)
+                if u.resid:
+                    live.add(u.resid)
+        self._last_contrib = {}
+        for u in self.units:
+            if u.out not in live:
+                continue
+            for t in tuple(u.srcs) + ((u.resid,) if u.resid else ()):
+                self._last_contrib.setdefault(t, u)
+        self.gm = {}             # tensor -> bf16 masked total gradient written by the fusing epilogue
+        self._fused = set()      # tensors whose producer's BatchNorm-backward sums come from a dgrad epilogue
 
         order = []  # static accumulation bookkeeping: which tensors already hold a gradient at each point
         have = set()
@@ -713,16 +739,22 @@ class Engine:
             b.relu = int(u.relu)
             b.raw_is_half = 1
             b.n, b.h, b.w, b.c = N, ho, wo, u.cout
+            bn_i = self._bn_idx[u.conv]
             b.sum_g, b.sum_gx = self.bn_sums_all[bn_i, 0].data_ptr(), self.bn_sums_all[bn_i, 1].data_ptr()
-            bn_i += 1
             b.dy = cu.dy.data_ptr()
             b.dilate = 0
             b.dgamma = self.grad[u.bn + ".weight"].data_ptr()
             b.dbeta = self.grad[u.bn + ".bias"].data_ptr()
-            self.bwd.append(self._call(L.gdn_bn_bwd_reduce, b, "bn_bwd_reduce " + u.conv))
+            if u.out in self._fused:
+                # the sums were reduced (and the ReLU mask applied) by the epilogue of the convolution that completed g_out
+                if u.out in self.gm:
+                    b.dact, b.dact_is_bf16, b.relu = self.gm[u.out].data_ptr(), 1, 0
+            else:
+                self.bwd.append(self._call(L.gdn_bn_bwd_reduce, b, "bn_bwd_reduce " + u.conv))
+                self.launches_bwd += 1
             self.bwd.append(self._call(L.gdn_act_backward, b, "act_backward " + u.conv))
             self.grad_ready_op[u.bn + ".weight"] = self.grad_ready_op[u.bn + ".bias"] = len(self.bwd) - 1
-            self.launches_bwd += 2
+            self.launches_bwd += 1
             # ---- weight gradient (same geometry as the forward conv)
             wd = WgradDesc()
             fd = cu.conv_desc
@@ -906,15 +938,23 @@ class Engine:
                 d.resid = pend.data_ptr()
             else:
                 d.resid = tgt.data_ptr() if acc else None
+            self._fuse_bn_backward_stats(d, u, s_name)
             self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
             self._dgrad_conv_end = len(self.bwd)
             self.launches_bwd += 1
         else:
-            tmp = torch.empty((N, d.out_h, d.out_w, cs), dtype=torch.float32, device=dev)
-            d.out_f32 = tmp.data_ptr()
+            # gradient w.r.t. the padded / upsampled / dilated operand buffer: bf16 (half the bytes of the largest
+            # intermediate of the backward pass; the fold sums <= 36 of them per source element in fp32)
+            tmp16 = cs % 4 == 0 and os.environ.get("GDN_FOLD_BF16", "1") != "0"
+            tmp = torch.empty((N, d.out_h, d.out_w, cs), dtype=torch.bfloat16 if tmp16 else torch.float32, device=dev)
+            if tmp16:
+                d.out_bf16 = Act(tmp.data_ptr(), N, d.out_h, d.out_w, cs, 0)
+            else:
+                d.out_f32 = tmp.data_ptr()
             self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
             self._dgrad_conv_end = len(self.bwd)
             f = FoldDesc()
+            f.dpad_is_bf16 = int(tmp16)
             f.dpad = tmp.data_ptr()
             f.ctot, f.c_off = cs, 0
             f.n, f.h, f.w, f.c = N, h_s, w_s, cs
@@ -925,6 +965,33 @@ class Engine:
             self.launches_bwd += 2
             cu.keep = getattr(cu, "keep", []) + [tmp]
         cu.keep = getattr(cu, "keep", []) + [wdg]
+
+    def _fuse_bn_backward_stats(self, d, u, s_name):
+        """d: a single-launch input-gradient descriptor of unit u that writes d(s_name) directly.  If it is the LAST
+        contribution to that gradient, let its epilogue reduce the BatchNorm-backward sums of the unit that produced
+        s_name (and apply that unit's ReLU mask); the gradient is then kept as bf16 only unless the producer's identity
+        branch still reads the fp32 value."""
+        if not (self.train and self.do_bwd and getattr(self, "_fuse_bnbwd", False)):
+            return
+        p = self.producer.get(s_name)
+        if p is None or p.bn is None or p.tanh or self._last_contrib.get(s_name) is not u:
+            return
+        if (p.relu and p.resid) or p.cout % 32 or d.cout != p.cout or d.dst_sy != 1 or d.dst_sx != 1:
+            return
+        cp = self.cu[p.conv]
+        bn_i = self._bn_idx[p.conv]
+        d.bwd_raw = cp.raw.data_ptr()
+        d.bwd_coef = cp.coef4.data_ptr()
+        d.bwd_relu = int(p.relu)
+        d.stat_sum = self.bn_sums_all[bn_i, 0].data_ptr()
+        d.stat_sqsum = self.bn_sums_all[bn_i, 1].data_ptr()
+        self._fused.add(s_name)
+        if not p.resid:
+            # nothing but the producer's BatchNorm backward reads this gradient: bf16, ReLU mask already applied
+            c, h, w = self.shape[s_name]
+            self.gm[s_name] = torch.empty((self.N, h, w, c), dtype=torch.bfloat16, device=self.dev)
+            d.out_f32 = None
+            d.out_bf16 = Act(self.gm[s_name].data_ptr(), self.N, h, w, c, 0)
 
     def _build_dgrad_stride2(self, u, cu, s_name, c_off, cs, acc):
         """input gradient of a stride-2 convolution as FOUR stride-1 convolutions over dy (sub-pixel decomposition):
@@ -941,10 +1008,11 @@ class Engine:
         offb = cu.off + pad_phys
         Hd, Wd = h_s + 2 * pad_phys, w_s + 2 * pad_phys
         direct = not refl
+        tmp16 = (not direct) and cs % 4 == 0 and os.environ.get("GDN_FOLD_BF16", "1") != "0"
         if direct:
             tgt = self.dact[s_name]
         else:
-            tgt = torch.empty((N, Hd, Wd, cs), dtype=torch.float32, device=dev)
+            tgt = torch.empty((N, Hd, Wd, cs), dtype=torch.bfloat16 if tmp16 else torch.float32, device=dev)
         keep = []
         for ay in (0, 1):
             for ax in (0, 1):
@@ -971,7 +1039,10 @@ class Engine:
                 d.dst_h, d.dst_w = Hd, Wd
                 d.dst_sy = d.dst_sx = 2
                 d.dst_oy, d.dst_ox = oy, ox
-                d.out_f32 = tgt.data_ptr()
+                if tmp16:
+                    d.out_bf16 = Act(tgt.data_ptr(), N, Hd, Wd, cs, 0)
+                else:
+                    d.out_f32 = tgt.data_ptr()
                 d.resid = tgt.data_ptr() if (direct and acc) else None
                 if d.out_h > 0 and d.out_w > 0:
                     self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad " + u.conv))
@@ -981,6 +1052,7 @@ class Engine:
         if not direct:
             f = FoldDesc()
             f.dpad = tgt.data_ptr()
+            f.dpad_is_bf16 = int(tmp16)
             f.ctot, f.c_off = cs, 0
             f.n, f.h, f.w, f.c = N, h_s, w_s, cs
             f.pad, f.reflect, f.up, f.dilate = pad_phys, refl, 0, 0
@@ -1027,6 +1099,7 @@ class Engine:
         tgt = self.dact[src]
         d.out_f32 = tgt.data_ptr()
         d.resid = tgt.data_ptr() if acc else None
+        self._fuse_bn_backward_stats(d, u, src)
         self.bwd.append(self._call(L.gdn_conv2d, d, "dgrad head"))
         # weight gradient: dw[0][c][t'] = sum_q x[q][c] * dcol[q][t']
         v = self._variant(u)

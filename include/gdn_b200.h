@@ -82,6 +82,16 @@ typedef struct {
   double* stat_sqsum;        /* [cout] += sum of acc^2 */
   int32_t out16_is_half;     /* store out_bf16 as IEEE fp16 instead (pre-BatchNorm conv outputs: they only feed
                                 elementwise kernels, and fp16's 10-bit mantissa keeps BN's mean subtraction accurate) */
+  /* Fused BatchNorm(+ReLU)-backward statistics, for an input-gradient launch that writes the LAST contribution to the
+   * gradient of a tensor t (the caller knows the order of its backward plan).  With v = acc (+ resid) the total gradient:
+   *   g = v * [fma(raw, scale, shift) > 0]   (only when bwd_relu);   stat_sum[co] += sum g;   stat_sqsum[co] += sum g*xhat,
+   *   xhat = (raw - mean) * rstd;   the stores then write g (fp32 and / or bf16)
+   * -- exactly what gdn_bn_bwd_reduce computes from the fp32 gradient, without the extra pass over it.
+   * bwd_raw: fp16 pre-BN output of the unit that PRODUCED t, [n][dst_h][dst_w][cout]; bwd_coef: that unit's
+   * (scale, shift, mean, rstd) per channel as written by gdn_bn_finalize(coef4).  Needs cout % 32 == 0. */
+  const void* bwd_raw;       /* NULL = off (then stat_sum / stat_sqsum are the forward statistics above) */
+  const float* bwd_coef;
+  int32_t bwd_relu;
 } gdn_conv_desc;
 
 int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream);
@@ -104,10 +114,11 @@ int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, int kh, 
                int kpad, gdn_stream stream);
 
 /* batch statistics -> per-channel scale = gamma*rstd, shift = beta - mean*scale; saves mean / rstd for backward;
- * updates running stats (momentum, unbiased variance) when running_mean != NULL. */
+ * updates running stats (momentum, unbiased variance) when running_mean != NULL.  coef4 (optional, 16-byte aligned
+ * [c][4] floats) receives (scale, shift, mean, rstd) interleaved: the operand of gdn_conv_desc.bwd_coef. */
 int gdn_bn_finalize(const double* sum, const double* sqsum, double count, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* mean, float* rstd, int c, gdn_stream stream);
+                    float* mean, float* rstd, float* coef4, int c, gdn_stream stream);
 /* eval mode: scale = gamma / sqrt(running_var + eps), bias = beta - running_mean*scale */
 int gdn_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, float* scale,
                 float* bias, int c, gdn_stream stream);
@@ -135,7 +146,7 @@ int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream);
  * apply (gdn_act_backward): dy = scale*(g - sum_g/n - xhat*sum_gx/n) as bf16 (optionally zero-dilated x2),
  * dgamma += sum_gx, dbeta += sum_g. */
 typedef struct {
-  const float* dact;
+  const void* dact;        /* fp32 [n][h][w][c], or bf16 when dact_is_bf16 */
   const void* raw;
   const float* scale;
   const float* shift;
@@ -150,6 +161,7 @@ typedef struct {
   float* dgamma;
   float* dbeta;
   int32_t raw_is_half;
+  int32_t dact_is_bf16;    /* dact is the bf16 buffer a gdn_conv2d epilogue wrote in bwd_stats mode (ReLU mask applied) */
 } gdn_bn_bwd_desc;
 int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream);
 int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream);
@@ -174,12 +186,13 @@ int gdn_act_backward_frozen(const gdn_frozen_bwd_desc* d, gdn_stream stream);
  * source activation gradient dact [n][h][w][c] (+= when accumulate).  Channel counts that are not multiples of 4
  * (the 1- / 3-channel network input) are supported for reflection / zero padding only. */
 typedef struct {
-  const float* dpad;
+  const void* dpad;        /* fp32, or bf16 when dpad_is_bf16 (written by gdn_conv2d through out_bf16) */
   int32_t ctot, c_off;
   int32_t n, h, w, c;
   int32_t pad, reflect, up, dilate;
   float* dact;
   int32_t accumulate;
+  int32_t dpad_is_bf16;
 } gdn_fold_desc;
 int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream);
 

@@ -152,7 +152,7 @@ class EmulatedLib:
         crop = Xn[:, :, ylo + pt: yhi + pt + 1, xlo + pl: xhi + pl + 1]
         acc = F.conv2d(crop, Wc, stride=st)[:, :d.cout].permute(0, 2, 3, 1).contiguous()   # (n, out_h, out_w, cout)
         assert acc.shape[1:3] == (d.out_h, d.out_w)
-        if d.stat_sum:
+        if d.stat_sum and not d.bwd_raw:
             _t(d.stat_sum, (d.cout,), torch.float64).add_(acc.double().sum((0, 1, 2)))
             _t(d.stat_sqsum, (d.cout,), torch.float64).add_((acc.double() ** 2).sum((0, 1, 2)))
         v = acc
@@ -166,6 +166,16 @@ class EmulatedLib:
         assert d.dst_oy + (d.out_h - 1) * sy < d.dst_h and d.dst_ox + (d.out_w - 1) * sx < d.dst_w
         if d.resid:
             v = v + _t(d.resid, (n, d.dst_h, d.dst_w, d.cout), torch.float32)[:, ys, xs]
+        if d.bwd_raw:
+            # fused BatchNorm(+ReLU)-backward statistics of the unit that produced the destination tensor (header comment)
+            assert d.cout == d.cout_pad and d.cout % 32 == 0 and not d.tanh_out and not d.out16_is_half
+            raw = _t(d.bwd_raw, (n, d.dst_h, d.dst_w, d.cout), torch.float16)[:, ys, xs].float()
+            cf = _t(d.bwd_coef, (d.cout, 4), torch.float32)
+            if d.bwd_relu:
+                v = v * ((raw * cf[:, 0] + cf[:, 1]) > 0)
+            xhat = (raw - cf[:, 2]) * cf[:, 3]
+            _t(d.stat_sum, (d.cout,), torch.float64).add_(v.double().sum((0, 1, 2)))
+            _t(d.stat_sqsum, (d.cout,), torch.float64).add_((v * xhat).double().sum((0, 1, 2)))
         if d.tanh_out:
             v = torch.tanh(v)
         if d.out_f32:
@@ -231,7 +241,8 @@ class EmulatedLib:
         f = _obj(fref)
         sc = 2 if (f.up or f.dilate) else 1
         Hq, Wq = f.h * sc + 2 * f.pad, f.w * sc + 2 * f.pad
-        dpad = _t(f.dpad, (f.n, Hq, Wq, f.ctot), torch.float32)[..., f.c_off:f.c_off + f.c].permute(0, 3, 1, 2)
+        dpad = _t(f.dpad, (f.n, Hq, Wq, f.ctot), torch.bfloat16 if f.dpad_is_bf16 else torch.float32).float()
+        dpad = dpad[..., f.c_off:f.c_off + f.c].permute(0, 3, 1, 2)
         with torch.enable_grad():             # the adjoint of the input transform, by autograd of the transform itself
             x = torch.zeros((f.n, f.c, f.h, f.w), requires_grad=True)
             z = x
@@ -253,7 +264,8 @@ class EmulatedLib:
         return 0
 
     # ---- training mode: batch statistics, BatchNorm backward, weight gradients
-    def _e_bn_finalize(self, sum_, sqsum, count, gamma, beta, eps, momentum, rmean, rvar, scale, shift, mean, rstd, c, s):
+    def _e_bn_finalize(self, sum_, sqsum, count, gamma, beta, eps, momentum, rmean, rvar, scale, shift, mean, rstd, coef4,
+                       c, s):
         count, eps, momentum = (v.value if hasattr(v, "value") else v for v in (count, eps, momentum))
         m = _t(sum_, (c,), torch.float64) / count
         var = _t(sqsum, (c,), torch.float64) / count - m * m
@@ -263,6 +275,9 @@ class EmulatedLib:
         _t(shift, (c,), torch.float32).copy_((b - m * g * rs).float())
         _t(mean, (c,), torch.float32).copy_(m.float())
         _t(rstd, (c,), torch.float32).copy_(rs.float())
+        if _addr(coef4):
+            _t(coef4, (c, 4), torch.float32).copy_(torch.stack([(g * rs).float(), (b - m * g * rs).float(), m.float(),
+                                                                  rs.float()], 1))
         if _addr(rmean):
             rm, rv = _t(rmean, (c,), torch.float32), _t(rvar, (c,), torch.float32)
             rm.mul_(1 - momentum).add_((momentum * m).float())
@@ -271,7 +286,7 @@ class EmulatedLib:
 
     def _bn_bwd_terms(self, b):
         shp = (b.n, b.h, b.w, b.c)
-        g = _t(b.dact, shp, torch.float32).clone()
+        g = _t(b.dact, shp, torch.bfloat16).float() if b.dact_is_bf16 else _t(b.dact, shp, torch.float32).clone()
         raw = _t(b.raw, shp, torch.float16 if b.raw_is_half else torch.bfloat16).float()
         sc, sh = _t(b.scale, (b.c,), torch.float32), _t(b.shift, (b.c,), torch.float32)
         if b.relu:

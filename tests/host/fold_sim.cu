@@ -9,7 +9,7 @@ using namespace gdn;
 
 extern "C" int fold_rows2_host(const float* dpad, int ctot, int c_off, int N, int H, int W, int C, int P, int reflect, int up,
                                int dilate, float* dact, int accumulate, int nthreads, int nblocks) {
-  FoldK f{dpad, ctot, c_off, N, H, W, C, P, reflect, up, dilate, dact, accumulate};
+  FoldK f{dpad, ctot, c_off, N, H, W, C, P, reflect, up, dilate, dact, accumulate, 0};
   int lg_cg = -1;
   for (int l = 0; l < 16; l++)
     if ((1 << l) == C / 4) lg_cg = l;

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from tests.abi_emulator import emulated_abi, engine_forward, run_ops
-from tests.util import build_module, shapes_of, relerr
+from tests.util import build_module, shapes_of, relerr, engine_act_grad
 
 H, W, B = 32, 64, 2
 
@@ -129,7 +129,7 @@ def test_training_plan_forward_backward_matches_autograd(gname):
         assert relerr(eng.value_nchw(n), T[n].float()) <= 8e-2, n
     for u in g.units:
         if u.out != "out" and T[u.out].grad is not None:
-            a, b = eng.dact[u.out].permute(0, 3, 1, 2), T[u.out].grad.float()
+            a, b = engine_act_grad(eng, u.out, T[u.out].grad.float(), masks)
             assert _l2rel(a, b) <= 3e-2, u.out
     checked = 0
     for k, v in sd64.items():
@@ -138,6 +138,8 @@ def test_training_plan_forward_backward_matches_autograd(gname):
         assert _l2rel(eng.grad[k], v.grad.float()) <= 3e-2, k
         checked += 1
     assert checked >= 2 * len(g.units) - 2
+    # most BatchNorm-backward reductions ride on the epilogue of the convolution that completes the gradient
+    assert len(eng._fused) >= len(g.units) // 2 and len(eng.gm) >= 1, (sorted(eng._fused), sorted(eng.gm))
 
 
 def test_instance_norm_branch_eval_is_running_stat_normalisation():

@@ -144,6 +144,15 @@ def test_bn_backward_reduce_and_apply(shape, relu, half):
     assert l2(dbeta.double(), bd.grad) <= 1e-3
     assert l2(dgamma.double(), gd.grad) <= 1e-3
     assert l2(dy.double().permute(0, 3, 1, 2), x.grad) <= 6e-3
+    # apply pass from a PRE-MASKED bf16 gradient with the sums already reduced (the fused-statistics plan): same dy
+    mask = ((raw16.float() * scale + shift) > 0) if relu else torch.ones_like(dact, dtype=torch.bool)
+    gm = (dact * mask).bfloat16()
+    dy2 = torch.full((n, h, w, c), float("nan"), device=dev, dtype=torch.bfloat16)
+    b.dact, b.dact_is_bf16, b.relu, b.dy = gm.data_ptr(), 1, 0, dy2.data_ptr()
+    b.dgamma = b.dbeta = None
+    _lib.check(L.gdn_act_backward(C.byref(b), _lib.stream_ptr()), "act_backward bf16")
+    torch.cuda.synchronize()
+    assert l2(dy2.double().permute(0, 3, 1, 2), x.grad) <= 8e-3
 
 
 FOLD_CASES = [
@@ -180,6 +189,17 @@ def test_fold_grad_is_the_adjoint_of_the_input_transform(case):
     _lib.check(L.gdn_fold_grad(C.byref(f), _lib.stream_ptr()), "fold")
     torch.cuda.synchronize()
     assert (dact.double() - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    # the same adjoint from a bf16 operand gradient (what the input-gradient convolutions write): identical arithmetic on
+    # the bf16-rounded values
+    d16 = dpad.bfloat16()
+    x2 = torch.zeros((n, c, h, w), dtype=torch.float64, device=dev, requires_grad=True)
+    _transform(x2, pad, reflect, up, dilate).backward(d16[..., c_off:c_off + c].double().permute(0, 3, 1, 2))
+    want2 = x2.grad.permute(0, 2, 3, 1) + (prev.double() if acc else 0)
+    dact2 = prev.clone()
+    f.dpad, f.dpad_is_bf16, f.dact = d16.data_ptr(), 1, dact2.data_ptr()
+    _lib.check(L.gdn_fold_grad(C.byref(f), _lib.stream_ptr()), "fold bf16")
+    torch.cuda.synchronize()
+    assert (dact2.double() - want2).abs().max().item() <= 1e-5 * want2.abs().max().item()
 
 
 @pytest.mark.parametrize("n,c,h,w,k,pad,reflect,kpad", [(2, 3, 16, 24, 9, 4, 1, 256), (2, 1, 12, 20, 9, 4, 1, 128),

@@ -184,3 +184,64 @@ def test_fp32_only_epilogue_strided_destination(cin, cout, k, stride2dst, resid,
     assert (got - want).abs().max().item() <= 1e-3 * ref.abs().max().item()
     if stride2dst:                                   # positions between the strided destinations stay untouched
         assert torch.isnan(out[:, 0::2, 1::2]).all()
+
+
+@pytest.mark.parametrize("cin,cout,k,relu,resid,keep32,algo,N,H,W", [
+    (64, 64, 3, True, False, False, 0, 2, 24, 40),
+    (128, 64, 1, True, True, False, 0, 2, 24, 40),
+    (64, 128, 3, False, True, True, 2 | (2 << 8), 3, 16, 24),
+    (512, 512, 3, True, False, False, 1 | (1 << 24), 4, 8, 26),
+    (64, 64, 9, True, True, False, 2 | (4 << 8) | (1 << 24), 4, 64, 96)])
+def test_fused_bn_backward_statistics_epilogue(cin, cout, k, relu, resid, keep32, algo, N, H, W):
+    """gdn_conv_desc.bwd_raw: the input-gradient launch that completes a tensor's gradient applies the producer's ReLU mask
+    and reduces sum g / sum g*xhat in its epilogue.  Against the separate path: fp64 conv (+ accumulate), mask from the
+    same fma expression, sums in fp64; outputs are the masked gradient as bf16 (and fp32 when the identity branch needs it)"""
+    import torch.nn.functional as F
+    from gdn_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(cin + cout + k + H)
+    p = k // 2
+    dy = (torch.rand((N, cin, H, W), generator=g) * 2 - 1).to(dev).to(torch.bfloat16)
+    w = ((torch.rand((cout, cin, k, k), generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16)
+    tot = F.conv2d(dy.double(), w.double(), None, 1, p).permute(0, 2, 3, 1)                 # NHWC fp64
+    r = (torch.rand((N, H, W, cout), generator=g) - 0.5).to(dev) if resid else None
+    if resid:
+        tot = tot + r.double()
+    raw = (torch.randn((N, H, W, cout), generator=g) * 1.5 + 0.2).to(dev).half()
+    coef = torch.stack([torch.rand(cout, generator=g) + 0.5, torch.rand(cout, generator=g) - 0.5,
+                        torch.rand(cout, generator=g) * 0.4, torch.rand(cout, generator=g) + 0.5], 1).to(dev).contiguous()
+    rawf = raw.float()
+    y64 = rawf.double() * coef[:, 0].double() + coef[:, 1].double()
+    mask = (y64 > 0) if relu else torch.ones_like(rawf, dtype=torch.bool)
+    safe = (y64.abs() > 1e-5) if relu else mask          # a mask test at fp32 rounding level may legitimately flip
+    xhat = ((rawf - coef[:, 2]) * coef[:, 3]).double()
+    gmask = tot * mask
+    want_s1, want_s2 = gmask.sum((0, 1, 2)), (gmask * xhat).sum((0, 1, 2))
+    sums = torch.zeros((2, cout), dtype=torch.float64, device=dev)
+    out16 = torch.full((N, H, W, cout), float("nan"), device=dev, dtype=torch.bfloat16)
+    out32 = torch.full((N, H, W, cout), float("nan"), device=dev) if keep32 else None
+    d = _lib.ConvDesc()
+    xb = dy.permute(0, 2, 3, 1).contiguous()
+    d.src0 = _lib.Act(xb.data_ptr(), N, H, W, cin, 0)
+    wp = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).contiguous()
+    d.weights = wp.data_ptr()
+    d.kh = d.kw = k
+    d.stride = 1
+    d.off_y = d.off_x = -p
+    d.out_h, d.out_w, d.cout, d.cout_pad, d.algo = H, W, cout, cout, algo
+    d.dst_h, d.dst_w, d.dst_sy, d.dst_sx = H, W, 1, 1
+    d.resid = r.data_ptr() if resid else None
+    d.out_bf16 = _lib.Act(out16.data_ptr(), N, H, W, cout, 0)
+    d.out_f32 = out32.data_ptr() if keep32 else None
+    d.bwd_raw, d.bwd_coef, d.bwd_relu = raw.data_ptr(), coef.data_ptr(), int(relu)
+    d.stat_sum, d.stat_sqsum = sums[0].data_ptr(), sums[1].data_ptr()
+    _lib.check(_lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
+    torch.cuda.synchronize()
+    scale_ = tot.abs().max().item()
+    # elements whose mask test sits at rounding level cannot flip here (the mask comes from the same stored fp16 / fp32 values)
+    assert ((out16.double() - gmask) * safe).abs().max().item() <= (2 ** -8) * scale_
+    if keep32:
+        assert ((out32.double() - gmask) * safe).abs().max().item() <= 1e-3 * scale_
+    for got, want in ((sums[0], want_s1), (sums[1], want_s2)):
+        assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-6, (got - want).abs().max().item()
+    d.bwd_coef = None
+    assert _lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()) == -1            # incomplete descriptor is refused
