@@ -34,12 +34,6 @@ GFLOP_RTOD_TRAIN = 1595.2   # per image, canonical: 3 x 414.75 + 
 GFLOP_RTOD_INFER = 414.75 + 175.48
 GFLOP_DTOD_TRAIN = 3 * 339.17
 FULL_H, FULL_W = 384, 1248   # KITTI 375x1242 padded to multiples of 16 (no reference network accepts 375x1242)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the bench shape (B = 20) from
-# the committed `ncu --set full` capture (profiles/r01m_ncu_conv.summary.txt: conv_igemm_kernel<64, 2>, 137.1 MB
-# read + 88.2 MB written while the kernel runs -- part of the output is still in L2 when it ends).  Algorithmic
-# bytes: 136.3 MB in (bf16 NHWC) + 136.3 MB out (fp16 raw) + 0.66 MB weights -- DESIGN.md section 6.
-DOMINANT_CONV_TRAFFIC_BYTES = 225.3e6
-
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -173,12 +167,92 @@ def cpu_step_fn(B):
     return step
 
 
+def torch_gpu_step_fn(dev, B, bf16):
+    """the same RtoD training step with torch ops on the GPU (oracle port -> cuDNN / ATen): the library baseline of
+    BASELINE.md 2b / SURVEY.md 8d.  bf16=False: fp32 with TF32 disabled (the parity oracle's arithmetic);
+    bf16=True: autocast + channels_last, the strongest off-the-shelf configuration.  Canonical accounting like the
+    product arm: the frozen DtoD passes stop after the encoder (what the loss consumes)."""
+    from oracle import model as OM, losses as OL, synth
+    from tests.util import shapes_of
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(shapes_of("AutoEncoder_2"), seed=0, bn_random=False).items()}
+    sdd = {k: v.to(dev) for k, v in synth.synth_state_dict(shapes_of("AutoEncoder_DtoD"), seed=1, bn_random=False).items()}
+    if bf16:
+        for d in (sd, sdd):
+            for k, v in d.items():
+                if v.dim() == 4:
+                    d[k] = v.contiguous(memory_format=torch.channels_last)
+    pn = [k for k in sd if sd[k].dtype == torch.float32 and not k.endswith(("running_mean", "running_var"))]
+    for k in pn:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in pn], 2e-5, (0.9, 0.999), eps=1e-8, weight_decay=5e-4, fused=True)
+    rgb, dep, spa = [t.to(dev) for t in synth_batch(B, 0)]
+    if bf16:
+        rgb = rgb.contiguous(memory_format=torch.channels_last)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            out = OM.autoencoder_2(sd, rgb, istrain=False, train=True, update_running=True)
+            with torch.no_grad():
+                ft_tar = OM.autoencoder_dtod(sdd, dep, encoder_only=True)
+                ft = OM.autoencoder_dtod(sdd, out.float(), encoder_only=True)
+        terms = OL.rtod_loss(out.float(), dep, spa, rgb.float(), [f.float() for f in ft], [f.float() for f in ft_tar])
+        opt.zero_grad(set_to_none=True)
+        terms["loss"].backward()
+        opt.step()
+        return terms["loss"]
+    return step
+
+
+def gpu_library_baseline(dev, B, steps=5):
+    """-> {"fp32_notf32": img/s, "bf16_channels_last": img/s, ...}: torch 2.11 / cuDNN on the same GPU, same step, same
+    batch, same run (CUDA events, 3 warm-up steps with cudnn.benchmark like the reference, GDN_main.py:31)"""
+    res = {"unit": "images/s", "batch": B, "steps": steps,
+           "what": "the same RtoD training step with torch ops (F.conv2d / batch_norm / interpolate -> cuDNN, autograd, "
+                   "fused torch Adam) via the oracle port of the reference classes; the reference tree is absent on the GPU box"}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for key, bf16 in (("fp32_notf32", False), ("bf16_channels_last", True)):
+            step = torch_gpu_step_fn(dev, B, bf16)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            res[key] = B / (e0.elapsed_time(e1) / steps / 1e3)
+            del step
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return res
+
+
+def dominant_conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (64->64 k9 conv, B = 20) from
+    the committed ncu --set full capture: profiles/dominant_conv_traffic.json, written by tools/ncu_summary.py from the
+    .ncu-rep of tools/profile_conv.py.  None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "dominant_conv_traffic.json")
+    if not os.path.isfile(p):
+        return None, None
+    d = json.load(open(p))
+    return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+
+
+CPU_SAMPLE_BATCH = 4
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = 2
+    B = CPU_SAMPLE_BATCH
     step = cpu_step_fn(B)
     for _ in range(args.warmup):
         step()
@@ -191,17 +265,21 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "RtoD train imgs/s @128x416", "value": v, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        # same config as the product arm (the workload measured); each CPU step is a BOUNDED SAMPLE of it, stated below
         "config": {"workload": RTOD_TRAIN_WORKLOAD % 20, "batch_per_gpu": 20, "parallelism": "dp%d" % args.gpus,
-                   "l2": "n/a (CPU arm)", "cpu_sample_batch": B},
+                   "l2": L2_NOTE},
+        "reference_sample": "each timed step processes %d images (not 20): images/s = %d / step time" % (B, B),
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "batch %d per step, fp32 torch CPU ops via the oracle port of the reference step "
-                                   "(/root/reference is not present on the GPU box)" % B},
+                         "sample": "every step = the whole RtoD training step on a batch of %d of the 20 images (fp32 torch "
+                                   "CPU ops, all host threads) via the oracle port of trainer.py:696-768; /root/reference is "
+                                   "not present on the GPU box" % B},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+L2_NOTE = "working set per step (GBs of activations) >> 126 MB L2; no explicit flush"
 RTOD_TRAIN_WORKLOAD = ("RtoD training step, batch %d per GPU, 128x416 (BASELINE configs[3]): AutoEncoder_2 fwd + 2 frozen "
                        "DtoD encoder passes + loss + bwd + fused Adam")
 _REAL_STDOUT = None
@@ -236,6 +314,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "train_guided", "train_dtod", "infer", "infer_fullres", "demo"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -405,9 +484,10 @@ def main():
         burst, sustained, hbm, src = peaks()
         cms, cfl, calgo = time_dominant_conv(dev, B)
         achieved = cfl / (cms / 1e3) / 1e12
+        traffic, traffic_src = dominant_conv_traffic()
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<64> (64->64 k9 s1, halo-resident)", "achieved": achieved,
                 "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
-                "traffic": DOMINANT_CONV_TRAFFIC_BYTES if B == 20 else None,
+                "traffic": traffic if B == 20 else None, "traffic_source": traffic_src,
                 "peak_source": src + " burst bf16 (kernel timed alone)", "ms_per_launch": cms,
                 "variant": "algo 0x%x (%s, J=%d%s)" % (calgo, "halo" if (calgo & 0xff) == 2 else "tapbox", (calgo >> 8) & 0xff,
                                                        ", CTA pairs cta_group::2" if calgo & (1 << 24) else ""),
@@ -417,16 +497,19 @@ def main():
         if world == 1 and not args.no_cpu_baseline and args.workload == "train":   # rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            cstep = cpu_step_fn(2)
+            cstep = cpu_step_fn(CPU_SAMPLE_BATCH)
             cstep()
             nrep, t0 = 0, time.perf_counter()
-            while nrep < 3 or (time.perf_counter() - t0 < 10.0 and nrep < 8):
+            while nrep < 3 or (time.perf_counter() - t0 < 12.0 and nrep < 8):
                 cstep()
                 nrep += 1
             dt = (time.perf_counter() - t0) / nrep
-            cpu = {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": "1 warm-up + %d timed RtoD training steps at batch 2 (fp32 torch CPU ops with all host "
-                             "threads, oracle port of trainer.py:696-768)" % nrep}
+            cpu = {"value": CPU_SAMPLE_BATCH / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "1 warm-up + %d timed RtoD training steps on a batch of %d of the 20 images (fp32 torch CPU ops "
+                             "with all host threads, oracle port of trainer.py:696-768)" % (nrep, CPU_SAMPLE_BATCH)}
+        lib = None
+        if world == 1 and not args.no_gpu_baseline and args.workload == "train":
+            lib = gpu_library_baseline(dev, B)
         eng = getattr(locals().get("stepper", None), "eng", None)
         if args.workload in ("train", "train_guided"):
             per_step = (eng.launches_fwd + eng.launches_bwd + len(eng.pack_ops) + len(eng.pack_ops_bwd) +
@@ -445,7 +528,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": B, "parallelism": "dp%d" % world,
-                       "l2": "working set per step (GBs of activations) >> 126 MB L2; no explicit flush"},
+                       "l2": L2_NOTE},
             "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": per_step * args.steps,
             "clocks": clocks,
@@ -453,6 +536,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if lib is not None:
+            line["gpu_library_baseline"] = lib
         emit(line)
     if world > 1:
         # CUDA graphs holding captured NCCL kernels are still alive: communicator teardown can dead-lock behind them

@@ -13,6 +13,7 @@ Reference: /root/reference/src/AE_model_unet.py:312-368,527-574; src/trainer.py:
 """
 import argparse
 import sys
+import time
 
 import torch
 
@@ -25,6 +26,14 @@ dev = "cuda"
 def no_tf32():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True          # the reference sets it (GDN_main.py:31)
+
+
+T0 = time.time()
+
+
+def stamp(msg):
+    print("[%.1f s] %s" % (time.time() - T0, msg), flush=True)
 
 
 def inputs_for(name, b, h, w, seed):
@@ -123,6 +132,11 @@ def probe_grad(name, kind, b, h, w):
             continue
         rows.append((k, c32, c16, cc))
     import statistics as st
+    tot = sum(g32[k].double().norm().item() ** 2 for k, *_ in rows) ** 0.5
+    bad = [(k, c[1][0], g32[k].double().norm().item() / tot) for k, *c in [(r[0], r[1]) for r in rows] if c[0][0] < 0.99]
+    print("grad %-17s %-6s tensors with cos(fp32) < 0.99: %d of %d; largest |g_ref|/|g_total| among them %.2e : %s"
+          % (name, kind, len(bad), len(rows), max([b[2] for b in bad] + [0.0]),
+             sorted(bad, key=lambda b: -b[2])[:4]), flush=True)
     for tag, idx in (("engine-vs-fp32", 1), ("engine-vs-bf16oracle", 2), ("bf16oracle-vs-fp32", 3)):
         cos = [r[idx][0] for r in rows]
         l2 = [r[idx][1] for r in rows]
@@ -160,7 +174,7 @@ class TorchRtoDStep:
         self.opt.zero_grad(set_to_none=True)
         terms["loss"].backward()
         self.opt.step()
-        return {k: float(v) for k, v in terms.items()}
+        return {k: float(v.detach()) for k, v in terms.items()}
 
 
 def probe_traj(b, h, w, steps=50, lr=2e-5, kind="init", nbatch=4):
@@ -180,6 +194,7 @@ def probe_traj(b, h, w, steps=50, lr=2e-5, kind="init", nbatch=4):
     st = RtoDTrainStep(rtod, dtod, lr=lr)
     worst = {"loss": 0.0, "output_loss": 0.0, "smooth_loss": 0.0, "latent_loss": 0.0}
     worst16 = dict(worst)
+    stamp("trajectory start")
     for i in range(steps):
         bt = batches[i % nbatch]
         a = {k: float(v) for k, v in st.step(*bt).items()}
@@ -189,6 +204,7 @@ def probe_traj(b, h, w, steps=50, lr=2e-5, kind="init", nbatch=4):
             worst[k] = max(worst[k], abs(a[k] - r[k]) / (abs(r[k]) + 1e-12))
             worst16[k] = max(worst16[k], abs(r16[k] - r[k]) / (abs(r[k]) + 1e-12))
         if i < 5 or i % 10 == 9:
+            stamp("step %d" % i)
             print("traj step %2d  product loss %.6f (out %.6f lat %.6f sm %.6f) | torch-fp32 %.6f (out %.6f lat %.6f sm %.6f) | torch-bf16emu %.6f"
                   % (i, a["loss"], a["output_loss"], a["latent_loss"], a["smooth_loss"], r["loss"], r["output_loss"],
                      r["latent_loss"], r["smooth_loss"], r16["loss"]), flush=True)
