@@ -727,7 +727,10 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const
   }
 }
 
-// dy = scale * (g - mean(g) - xhat * mean(g xhat)), no dilation: flat item index == flat element index / 8
+// dy = scale * (g - mean(g) - xhat * mean(g xhat)), no dilation: flat item index == flat element index / 8.
+// U items in flight per thread: 2 with the fp32 gradient stream (96 B of loads per thread), 4 with the bf16 one (its
+// 32 B per item leave the kernel latency-bound at 2: 3.2 TB/s measured, profiles/r02c_profile_ops.log).
+template <int U>
 __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const BnBwd b, const int lg_cg, const int chunk) {
   const int cgm = (1 << lg_cg) - 1;
   const int c8 = (threadIdx.x & cgm) * 8;
@@ -753,14 +756,14 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
   const long long total = b.npix << lg_cg;
   const long long i0 = (long long)blockIdx.x * chunk;
   const long long i1 = (i0 + chunk < total) ? i0 + chunk : total;
-  for (long long it0 = i0 + threadIdx.x; it0 < i1; it0 += 2 * kEwThreads) {
-    float x[2][8], d[2][8];
-    const bool two = it0 + kEwThreads < i1;
-    bn_load8(b, (size_t)it0 * 8, x[0], d[0]);
-    if (two) bn_load8(b, (size_t)(it0 + kEwThreads) * 8, x[1], d[1]);
+  for (long long it0 = i0 + threadIdx.x; it0 < i1; it0 += U * kEwThreads) {
+    float x[U][8], d[U][8];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (u == 1 && !two) break;
+    for (int u = 0; u < U; u++)
+      if (it0 + u * kEwThreads < i1) bn_load8(b, (size_t)(it0 + u * kEwThreads) * 8, x[u], d[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (it0 + u * kEwThreads >= i1) break;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -1281,10 +1284,11 @@ GDN_API int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream) {
     if (lg >= 0) {
       const long long want = (long long)device_sm_count() * 8;
       long long chunk = (total + want - 1) / want;
-      chunk = (chunk + 2 * kEwThreads - 1) / (2 * kEwThreads) * (2 * kEwThreads);
+      chunk = (chunk + 4 * kEwThreads - 1) / (4 * kEwThreads) * (4 * kEwThreads);
       if (chunk < (1ll << 30)) {
         const int grid = (int)((total + chunk - 1) / chunk);
-        bn_bwd_apply_fast_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        if (b.dact_bf16) bn_bwd_apply_fast_kernel<4><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        else bn_bwd_apply_fast_kernel<2><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
         GDN_LAUNCH_CHECK("bn_bwd_apply_fast_kernel");
         return GDN_OK;
       }

@@ -978,6 +978,11 @@ class Engine:
             return
         if (p.relu and p.resid) or p.cout % 32 or d.cout != p.cout or d.dst_sy != 1 or d.dst_sx != 1:
             return
+        # launches with a short reduction (1x1 convolutions on the concatenation, the im2col'd head) are bound by their
+        # epilogue already: the extra epilogue work doubled their time on the B200 (profiles/r02c_profile_ops.log:
+        # 0.113 -> 0.248 ms, more than the reduce pass it replaces) -- those keep the separate reduction
+        if d.kh * d.kw * d.src0.c < int(os.environ.get("GDN_FUSE_BNBWD_MINK", "2048")):
+            return
         cp = self.cu[p.conv]
         bn_i = self._bn_idx[p.conv]
         d.bwd_raw = cp.raw.data_ptr()

@@ -132,11 +132,11 @@ def probe_grad(name, kind, b, h, w):
             continue
         rows.append((k, c32, c16, cc))
     import statistics as st
-    tot = sum(g32[k].double().norm().item() ** 2 for k, *_ in rows) ** 0.5
-    bad = [(k, c[1][0], g32[k].double().norm().item() / tot) for k, *c in [(r[0], r[1]) for r in rows] if c[0][0] < 0.99]
+    tot = sum(g32[r[0]].double().norm().item() ** 2 for r in rows) ** 0.5
+    bad = [(r[0], round(r[1][0], 4), g32[r[0]].double().norm().item() / tot) for r in rows if r[1][0] < 0.99]
     print("grad %-17s %-6s tensors with cos(fp32) < 0.99: %d of %d; largest |g_ref|/|g_total| among them %.2e : %s"
-          % (name, kind, len(bad), len(rows), max([b[2] for b in bad] + [0.0]),
-             sorted(bad, key=lambda b: -b[2])[:4]), flush=True)
+          % (name, kind, len(bad), len(rows), max([b[2] for b in bad] + [0.0]), sorted(bad, key=lambda b: -b[2])[:4]),
+          flush=True)
     for tag, idx in (("engine-vs-fp32", 1), ("engine-vs-bf16oracle", 2), ("bf16oracle-vs-fp32", 3)):
         cos = [r[idx][0] for r in rows]
         l2 = [r[idx][1] for r in rows]

@@ -19,12 +19,16 @@ def _act(t, pad):
 
 
 def _conv_case(N, H, W, cin, cout, k, stride=1, reflect=False, algo=0, relu=False, bias=False, resid=False, stats=False,
-               reflect_out=0, cin2=0, seed=0):
+               reflect_out=0, cin2=0, seed=0, pad=None, f32ref=False):
     from gdn_pytorch_b200 import _lib
     g = torch.Generator().manual_seed(seed)
-    p = k // 2
-    x = (torch.rand((N, cin + cin2, H, W), generator=g) * 2 - 1).to(dev).to(torch.bfloat16).double()
-    w = ((torch.rand((cout, cin + cin2, k, k), generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).double()
+    p = k // 2 if pad is None else pad
+    ref_dt = torch.float32 if f32ref else torch.float64     # bench-sized cases: fp32 cuDNN (TF32 off) instead of fp64
+    if f32ref:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    x = (torch.rand((N, cin + cin2, H, W), generator=g) * 2 - 1).to(dev).to(torch.bfloat16).to(ref_dt)
+    w = ((torch.rand((cout, cin + cin2, k, k), generator=g) * 2 - 1) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).to(ref_dt)
     xin = F.pad(x, (p,) * 4, mode="reflect") if reflect else x
     raw = F.conv2d(xin, w, None, stride, 0 if reflect else p)
     bufpad = p if reflect else 0
@@ -34,12 +38,12 @@ def _conv_case(N, H, W, cin, cout, k, stride=1, reflect=False, algo=0, relu=Fals
     b = r = None
     if bias:
         b = (torch.rand(cout, generator=g) - 0.5).to(dev)
-        ref = ref + b.double().view(1, -1, 1, 1)
+        ref = ref + b.to(ref_dt).view(1, -1, 1, 1)
     if relu:
         ref = F.relu(ref)
     if resid:
         r = (torch.rand((N, OH, OW, cout), generator=g) - 0.5).to(dev)
-        ref = ref + r.double().permute(0, 3, 1, 2)
+        ref = ref + r.to(ref_dt).permute(0, 3, 1, 2)
     d = _lib.ConvDesc()
     keep = [xbuf]
     if cin2:
@@ -76,13 +80,13 @@ def _conv_case(N, H, W, cin, cout, k, stride=1, reflect=False, algo=0, relu=Fals
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     assert not torch.isnan(out32).any()
-    assert (out32.permute(0, 3, 1, 2).double() - ref).abs().max().item() <= 1e-3 * scale
+    assert (out32.permute(0, 3, 1, 2).to(ref_dt) - ref).abs().max().item() <= 1e-3 * scale
     refp = (F.pad(ref, (P,) * 4, mode="reflect") if P else ref).permute(0, 2, 3, 1)
     assert not torch.isnan(outb.float()).any()
-    assert (outb.double() - refp).abs().max().item() <= 6e-3 * scale      # bf16 storage: 2^-8 relative
+    assert (outb.to(ref_dt) - refp).abs().max().item() <= 6e-3 * scale      # bf16 storage: 2^-8 relative
     if stats:
-        assert torch.allclose(ssum[0], raw.sum((0, 2, 3)), rtol=1e-4, atol=1e-3 * scale)
-        assert torch.allclose(ssum[1], (raw ** 2).sum((0, 2, 3)), rtol=1e-4)
+        assert torch.allclose(ssum[0], raw.double().sum((0, 2, 3)), rtol=1e-4, atol=1e-3 * scale * (10 if f32ref else 1))
+        assert torch.allclose(ssum[1], (raw.double() ** 2).sum((0, 2, 3)), rtol=1e-4)
 
 
 CONV_CASES = [
@@ -95,7 +99,8 @@ CONV_CASES = [
     dict(N=5, H=8, W=26, cin=512, cout=512, k=3, algo=1, relu=True, bias=True, resid=True, stats=True),
     dict(N=2, H=32, W=64, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1),
     dict(N=2, H=16, W=40, cin=256, cout=512, k=3, stride=2, algo=1),
-    dict(N=2, H=32, W=64, cin=64, cout=128, k=4, stride=2, reflect=True, algo=1),
+    dict(N=2, H=32, W=64, cin=64, cout=128, k=4, stride=2, reflect=True, algo=1, pad=1),
+    dict(N=3, H=16, W=40, cin=256, cout=512, k=4, stride=2, reflect=True, algo=1 | (1 << 24), pad=1, stats=True),
     dict(N=2, H=16, W=40, cin=128, cout=128, k=1, algo=1, cin2=128, stats=True),
     dict(N=2, H=32, W=64, cin=128, cout=64, k=7, reflect=True, algo=2, reflect_out=3),
     dict(N=2, H=32, W=64, cin=64, cout=1, k=9, algo=2),
@@ -113,15 +118,20 @@ CONV_CASES = [
     dict(N=2, H=32, W=64, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24)),
     dict(N=3, H=16, W=40, cin=256, cout=512, k=3, stride=2, algo=1 | (1 << 24), stats=True),
     dict(N=3, H=16, W=40, cin=128, cout=64, k=1, algo=1 | (1 << 24), cin2=128, stats=True),
+    # the bench configuration itself (B = 20, 128 x 416 and its coarser maps): the persistent loop over 8 320 pixel tiles,
+    # stage-ring wrap-around, the odd CTA-pair tail, and the shipped variants (pairs, J = 4 / 2 / 1)
+    dict(N=20, H=128, W=416, cin=64, cout=64, k=9, algo=2 | (4 << 8) | (1 << 24), stats=True, f32ref=True),
+    dict(N=20, H=128, W=416, cin=64, cout=64, k=9, algo=0, relu=True, bias=True, resid=True, f32ref=True),
+    dict(N=20, H=64, W=208, cin=128, cout=128, k=7, algo=2 | (2 << 8) | (1 << 24), stats=True, f32ref=True),
+    dict(N=20, H=16, W=52, cin=512, cout=512, k=3, algo=2 | (1 << 8) | (1 << 24), stats=True, f32ref=True),
+    dict(N=20, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24), stats=True, f32ref=True),
+    dict(N=20, H=128, W=416, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24), stats=True, f32ref=True),
+    dict(N=20, H=128, W=416, cin=64, cout=64, k=1, algo=1, cin2=64, stats=True, f32ref=True),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items()))
 def test_conv_forward_kernel(case):
-    if case.get("k") == 4:
-        c = dict(case)
-        # k4 s2 reflect-1 (DtoD down-convs): p = 1, not k // 2
-        pytest.skip("covered through the network tests (padding 1 with k 4)")
     _conv_case(**case)
 
 
