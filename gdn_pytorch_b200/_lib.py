@@ -28,6 +28,7 @@ class ConvDesc(C.Structure):
         ("dst_oy", C.c_int32), ("dst_ox", C.c_int32),
         ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("out16_is_half", C.c_int32),
         ("bwd_raw", C.c_void_p), ("bwd_coef", C.c_void_p), ("bwd_relu", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -54,6 +55,7 @@ def lib():
         L.gdn_version.restype = C.c_int
         L.gdn_sm_count.restype = C.c_int
         L.gdn_resize_u8_workspace.restype = C.c_size_t
+        L.gdn_conv2d_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 

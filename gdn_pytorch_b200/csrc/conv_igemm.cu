@@ -67,6 +67,12 @@ struct ConvK {
   const __half* bs_raw;      // fp16 [n][dst_h][dst_w][cout], NULL = off
   const float4* bs_coef;     // [cout]
   int bs_relu;
+  // split-K (small maps: fewer pixel tiles than SMs): work item = (channel block, K split, pixel tile); split s reduces
+  // the 64-channel chunks [s*chunks/ksplit, (s+1)*chunks/ksplit) and stores its fp32 partial tile to ws + s*ws_slab;
+  // conv_splitk_combine_kernel sums the partials in a fixed order and runs the epilogue operators
+  int ksplit;
+  float* ws;
+  size_t ws_slab;
 };
 
 struct Ring {
@@ -179,9 +185,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // work item -> (output-channel block, pixel tile); a pair works on pixel tiles 2m and 2m + 1 of the same block (the
   // odd one out lies beyond the last image: its loads are zero-filled, its pixels fail the `valid` test)
   const int cta_first = blockIdx.x / CG, cta_step = gridDim.x / CG;
-  auto decode = [&](int t, int& nblk, int& tx, int& ty, int& img) {
+  auto decode = [&](int t, int& nblk, int& tx, int& ty, int& img, int& ks) {
     nblk = t % p.cout_blocks;
     t /= p.cout_blocks;
+    ks = t % p.ksplit;
+    t /= p.ksplit;
     if (CG == 2) t = 2 * t + (int)cta_rank;
     tx = t % p.tiles_x;
     t /= p.tiles_x;
@@ -196,10 +204,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       Ring ra;
       for (int t = cta_first; t < p.total_tiles; t += cta_step) {
-        int nblk, tx, ty, img;
-        decode(t, nblk, tx, ty, img);
+        int nblk, tx, ty, img, ks;
+        decode(t, nblk, tx, ty, img, ks);
         const int oy0 = ty * tile_h, ox0 = tx * tile_w, n0 = img * p.nb;
-        for (int c = 0; c < chunks; c++) {
+        const int cpk = chunks / p.ksplit;
+        for (int c = ks * cpk; c < (ks + 1) * cpk; c++) {
           const bool s1 = c >= p.chunks0;
           const CUtensorMap* tm = s1 ? &tmA1 : &tmA0;
           const int cc = s1 ? c - p.chunks0 : c;
@@ -242,9 +251,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (lane == 0) {
       Ring rb;
       for (int t = cta_first; t < p.total_tiles; t += cta_step) {
-        int nblk, tx, ty, img;
-        decode(t, nblk, tx, ty, img);
-        for (int c = 0; c < chunks; c++)
+        int nblk, tx, ty, img, ks;
+        decode(t, nblk, tx, ty, img, ks);
+        const int cpk = chunks / p.ksplit;
+        for (int c = ks * cpk; c < (ks + 1) * cpk; c++)
           for (int tap = 0; tap < taps; tap++) {
             mbar_wait(&b_empty[rb.i], rb.ph ^ 1);
             if (CG == 2) {
@@ -291,7 +301,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride) + acc_j0;
         uint32_t accum = 0u;
-        for (int c = 0; c < chunks; c++) {
+        for (int c = 0; c < chunks / p.ksplit; c++) {
           if (halo) mbar_wait(&a_full[ra.i], ra.ph);
           uint32_t a_off = sA_u + (uint32_t)ra.i * a_bytes;   // halo: shifted window start, advanced tap by tap
           for (int r = 0; r < kh; r++) {
@@ -354,10 +364,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int m = q * 32 + lane;
     const bool do_bstats = p.bs_raw != nullptr;                  // sum g, sum g*xhat of the masked total gradient
     const bool do_stats = p.stat_sum != nullptr && !do_bstats;   // forward: sum x, sum x^2 of the raw accumulators
-    const bool any_stats = p.stat_sum != nullptr;
+    const bool any_stats = p.stat_sum != nullptr && p.ksplit == 1;
     for (int t = cta_first; t < p.total_tiles; t += cta_step) {
-      int nblk, tx, ty, img;
-      decode(t, nblk, tx, ty, img);
+      int nblk, tx, ty, img, ks;
+      decode(t, nblk, tx, ty, img, ks);
       mbar_wait(&acc_full[rc.i], rc.ph);
       tc_fence_after();
       const uint32_t acc_addr = tmem_base + (uint32_t)(rc.i * acc_stride) + ((uint32_t)(q * 32) << 16);
@@ -402,6 +412,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             for (int i = 0; i < CW; i++) v[i] = __uint_as_float(r[i]);
           }
           const int cb = nblk * BN + cc;
+          if (p.ksplit > 1) {
+            // partial sums only: the combine kernel owns bias / ReLU / residual / statistics / conversions
+            if (valid) {
+              float* wp = p.ws + (size_t)ks * p.ws_slab + pix * p.cout + cb;
+#pragma unroll
+              for (int i = 0; i < CW; i += 4)
+                *reinterpret_cast<float4*>(wp + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            continue;
+          }
           if (do_stats) {
             float s1[CW], s2[CW];
 #pragma unroll
@@ -561,6 +581,117 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------- split-K combine
+// Sums the ksplit fp32 partial tiles of a split-K convolution in a fixed order (s = 0, 1, ...: no atomics on the data
+// path) and applies the operators of the convolution epilogue: forward statistics of the raw sums, bias, ReLU, fp32
+// residual, fused BatchNorm-backward mask + statistics, fp32 / bf16 / fp16 stores.  One thread = 8 channels of a pixel;
+// a thread keeps the same 8 channels over its grid-stride loop, so the statistics stay in registers until the end.
+struct CombK {
+  const float* ws;
+  size_t slab;
+  int S;
+  long long npix;
+  int C;
+  const float* bias;
+  int relu;
+  const float* resid;
+  float* out_f32;
+  void* out16;
+  int half;
+  double* stat_sum;
+  double* stat_sq;
+  const __half* bs_raw;
+  const float4* bs_coef;
+  int bs_relu;
+};
+
+__global__ void __launch_bounds__(256) conv_splitk_combine_kernel(const CombK k) {
+  extern __shared__ float s_red[];   // [2][C]
+  const int cg = k.C >> 3;
+  const int c8 = (threadIdx.x & (cg - 1)) * 8;
+  const bool fstats = k.stat_sum && !k.bs_raw, bstats = k.bs_raw != nullptr;
+  if (k.stat_sum) {
+    for (int i = threadIdx.x; i < 2 * k.C; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+  }
+  float s1[8], s2[8], bi[8];
+  float4 cf[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    s1[j] = s2[j] = 0.f;
+    bi[j] = k.bias ? __ldg(k.bias + c8 + j) : 0.f;
+    cf[j] = bstats ? __ldg(k.bs_coef + c8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long total = k.npix * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const size_t off = (size_t)i * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < k.S; s++) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(k.ws + (size_t)s * k.slab + off));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(k.ws + (size_t)s * k.slab + off + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (fstats) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        s1[j] += v[j];
+        s2[j] = fmaf(v[j], v[j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      v[j] += bi[j];
+      if (k.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (k.resid) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(k.resid + off));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(k.resid + off + 4));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bstats) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(k.bs_raw + off));
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int h2 = 0; h2 < 4; h2++) {
+        const float2 xy = __half22float2(*reinterpret_cast<const __half2*>(&w4[h2]));
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = h2 * 2 + e;
+          const float x = e ? xy.y : xy.x;
+          if (k.bs_relu && fmaf(x, cf[j].x, cf[j].y) <= 0.f) v[j] = 0.f;
+          s1[j] += v[j];
+          s2[j] = fmaf(v[j], (x - cf[j].z) * cf[j].w, s2[j]);
+        }
+      }
+    }
+    if (k.out_f32) {
+      *reinterpret_cast<float4*>(k.out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(k.out_f32 + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (k.out16) {
+      uint4 o;
+      if (k.half) {
+        o = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+      } else {
+        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(k.out16) + off) = o;
+    }
+  }
+  if (k.stat_sum) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      atomicAdd(&s_red[c8 + j], s1[j]);
+      atomicAdd(&s_red[k.C + c8 + j], s2[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k.C; i += blockDim.x) {
+      atomicAdd(k.stat_sum + i, (double)s_red[i]);
+      atomicAdd(k.stat_sq + i, (double)s_red[k.C + i]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 static int ilog2(int v) {
   int l = 0;
@@ -618,6 +749,8 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
 }  // namespace gdn
 
 using namespace gdn;
+
+extern "C" __attribute__((visibility("default"))) size_t gdn_conv2d_workspace_bytes(const gdn_conv_desc* d);
 
 extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream) {
   if (!d || !d->src0.ptr || !d->weights) return fail(GDN_INVALID_DESC, "gdn_conv2d: null descriptor / source / weights");
@@ -697,6 +830,23 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
 
   int mode = d->algo & 0xff;
   const int cg = ((d->algo >> 24) & 1) ? 2 : 1;   // bit 24 of algo: CTA pairs (tcgen05 cta_group::2), HALO mode only
+  // bits 25-27 of algo: split-K factor (2 or 4) for maps with fewer pixel tiles than SMs; needs the caller's workspace
+  int ksplit = (d->algo >> 25) & 7;
+  if (ksplit < 2) ksplit = 1;
+  if (ksplit > 1) {
+    const int chunks_all = d->src0.c / 64 + (two ? d->src1.c / 64 : 0);
+    const size_t need = gdn_conv2d_workspace_bytes(d);
+    if ((ksplit != 2 && ksplit != 4) || chunks_all % ksplit || k.dst_sy != 1 || k.dst_sx != 1 || k.dst_oy || k.dst_ox ||
+        d->dst_h != d->out_h || d->dst_w != d->out_w || d->tanh_out || d->out_reflect || (d->out_bf16.ptr && d->out_bf16.pad) ||
+        d->cout != d->cout_pad || d->cout % 8 || (d->cout & (d->cout - 1)) || d->cout > 2048)
+      return fail(GDN_UNSUPPORTED_SHAPE, "gdn_conv2d: split-K %d not applicable to this launch", ksplit);
+    if (!d->workspace || d->workspace_bytes < need)
+      return fail(GDN_WORKSPACE_TOO_SMALL, "gdn_conv2d: split-K needs %zu bytes of workspace (got %zu)", need,
+                  (size_t)d->workspace_bytes);
+  }
+  k.ksplit = ksplit;
+  k.ws = reinterpret_cast<float*>(d->workspace);
+  k.ws_slab = (size_t)d->src0.n * d->out_h * d->out_w * d->cout;
   const int j_req = (d->algo >> 8) & 0xff;  // HALO: sub-tiles per tile requested by the caller's autotuner (0 = heuristic)
   const int taps = d->kh * d->kw;
   if (mode == GDN_CONV_AUTO)
@@ -783,17 +933,42 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   }
   const size_t smem = (size_t)k.na * k.a_bytes + (size_t)k.nbst * b_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
+  k.total_tiles *= k.ksplit;
   if (cg == 2) {
     switch (BN) {
-      case 64: return launch<64, 2>(tmA0, tmA1, tmB, k, smem, st);
-      case 128: return launch<128, 2>(tmA0, tmA1, tmB, k, smem, st);
-      default: return launch<256, 2>(tmA0, tmA1, tmB, k, smem, st);
+      case 64: rc = launch<64, 2>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 128: rc = launch<128, 2>(tmA0, tmA1, tmB, k, smem, st); break;
+      default: rc = launch<256, 2>(tmA0, tmA1, tmB, k, smem, st); break;
+    }
+  } else {
+    switch (BN) {
+      case 16: rc = launch<16, 1>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 64: rc = launch<64, 1>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 128: rc = launch<128, 1>(tmA0, tmA1, tmB, k, smem, st); break;
+      default: rc = launch<256, 1>(tmA0, tmA1, tmB, k, smem, st); break;
     }
   }
-  switch (BN) {
-    case 16: return launch<16, 1>(tmA0, tmA1, tmB, k, smem, st);
-    case 64: return launch<64, 1>(tmA0, tmA1, tmB, k, smem, st);
-    case 128: return launch<128, 1>(tmA0, tmA1, tmB, k, smem, st);
-    default: return launch<256, 1>(tmA0, tmA1, tmB, k, smem, st);
-  }
+  if (rc || k.ksplit == 1) return rc;
+  CombK c{};
+  c.ws = k.ws; c.slab = k.ws_slab; c.S = k.ksplit;
+  c.npix = (long long)d->src0.n * d->out_h * d->out_w;
+  c.C = d->cout;
+  c.bias = d->bias; c.relu = d->relu; c.resid = d->resid; c.out_f32 = d->out_f32;
+  c.out16 = d->out_bf16.ptr; c.half = d->out16_is_half;
+  c.stat_sum = d->stat_sum; c.stat_sq = d->stat_sqsum;
+  c.bs_raw = k.bs_raw; c.bs_coef = k.bs_coef; c.bs_relu = k.bs_relu;
+  const long long items = c.npix * (c.C / 8);
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  conv_splitk_combine_kernel<<<(int)blocks, 256, 2 * c.C * sizeof(float), st>>>(c);
+  GDN_LAUNCH_CHECK("conv_splitk_combine_kernel");
+  return GDN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t gdn_conv2d_workspace_bytes(const gdn_conv_desc* d) {
+  if (!d) return 0;
+  int ksplit = (d->algo >> 25) & 7;
+  if (ksplit < 2) return 0;
+  return (size_t)ksplit * d->src0.n * d->out_h * d->out_w * d->cout * sizeof(float);
 }

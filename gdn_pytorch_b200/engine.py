@@ -1136,6 +1136,22 @@ class Engine:
         self.launches_bwd += 5
         cu.keep = [wdg]
 
+    def _attach_splitk_workspace(self):
+        """one fp32 scratch buffer per engine for split-K launches (maps with fewer pixel tiles than SMs): every
+        convolution of an engine runs on one stream at a time, so they can share it.  Sized for split 4 of the largest
+        eligible launch; the library validates the rest (unsupported geometries return an error the autotuner skips)."""
+        need = 0
+        small = []
+        for what, d in self._conv_descs:
+            npix = d.src0.n * d.out_h * d.out_w
+            if npix <= 128 * 148 and d.cout == d.cout_pad and d.cout >= 64 and d.dst_sy == 1 and d.dst_sx == 1:
+                small.append(d)
+                need = max(need, 4 * npix * d.cout * 4)
+        self.splitk_ws = torch.empty(max(need, 16), dtype=torch.uint8, device=self.dev) if small else None
+        for d in small:
+            d.workspace = self.splitk_ws.data_ptr()
+            d.workspace_bytes = self.splitk_ws.numel()
+
     def autotune(self, reps=3):
         """Time every staging variant of every implicit-GEMM launch once, on the device, and keep the fastest.  All
         variants accumulate in the same order, so the choice changes speed only (tile shape vs. wave quantisation
@@ -1143,10 +1159,12 @@ class Engine:
         Runs at engine construction, before any real data is in the buffers; GDN_AUTOTUNE=0 keeps the heuristics."""
         self.algo_choice = {}
         cache = {}
+        if os.environ.get("GDN_SPLITK", "1") != "0":
+            self._attach_splitk_workspace()
         for what, d in self._conv_descs:
             key = (d.src0.n, d.src0.h, d.src0.w, d.src0.c, d.src0.pad, d.src1.c if d.src1.ptr else 0, d.kh, d.kw, d.stride,
                    d.out_h, d.out_w, d.cout_pad, bool(d.out_f32), bool(d.out_bf16.ptr), bool(d.resid), bool(d.stat_sum),
-                   d.dst_sy)
+                   d.dst_sy, bool(d.bwd_raw), bool(d.workspace), d.out_bf16.pad if d.out_bf16.ptr else 0)
             if key not in cache:
                 cache[key] = autotune_conv(self.L, d, reps, what)
             d.algo = cache[key]
@@ -1228,6 +1246,9 @@ class Engine:
 _PAIR = 1 << 24
 _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1,
           2 | (4 << 8) | _PAIR, 2 | (2 << 8) | _PAIR, 2 | (1 << 8) | _PAIR, 1 | _PAIR)
+_S2, _S4 = 2 << 25, 4 << 25     # split-K over the input-channel chunks (needs the engine's workspace)
+_ALGOS_SPLIT = (1 | _PAIR | _S2, 1 | _PAIR | _S4, 1 | _S2, 1 | _S4, 1 | (2 << 16) | _PAIR | _S2, 1 | (2 << 16) | _S2,
+                2 | (1 << 8) | _PAIR | _S2, 2 | (1 << 8) | _S2, 2 | (2 << 8) | (2 << 16) | _PAIR | _S2)
 _ALGOS_NARROW = (2 | (2 << 8) | (2 << 16), 2 | (1 << 8) | (2 << 16), 1 | (2 << 16),   # 128-wide channel tiles
                  2 | (2 << 8) | (2 << 16) | _PAIR, 2 | (1 << 8) | (2 << 16) | _PAIR, 1 | (2 << 16) | _PAIR)
 
@@ -1240,7 +1261,8 @@ def autotune_conv(L, d, reps=3, what="conv"):
     best, best_ms = 0, None
     # wide layers on small maps leave SMs idle with 256-channel tiles: let 128-wide tiles compete
     small = d.cout_pad >= 256 and d.src0.n * d.out_h * d.out_w * (d.cout_pad // 256) < 128 * 148 * 2
-    for algo in _ALGOS + (_ALGOS_NARROW if small else ()):
+    split = _ALGOS_SPLIT if (d.workspace and d.src0.n * d.out_h * d.out_w <= 128 * 148) else ()
+    for algo in _ALGOS + (_ALGOS_NARROW if small else ()) + split:
         if (algo & _PAIR) and not pairs_ok:
             continue
         d.algo = algo

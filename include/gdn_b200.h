@@ -67,7 +67,8 @@ typedef struct {
   int32_t cout;              /* real output channels */
   int32_t cout_pad;          /* channels in the weight tensor (multiple of 16; == cout unless cout < 16) */
   int32_t algo;              /* GDN_CONV_* in the low byte; bits 8-15: HALO sub-tiles per tile (1, 2, 4), bits 16-23: output-channel
-                                tile / 64 (1, 2, 4); 0 = library heuristic.  Every choice produces bit-identical
+                                tile / 64 (1, 2, 4); bit 24: CTA pairs; bits 25-27: split-K (see workspace);
+                                0 = library heuristic.  Every choice WITHOUT split-K produces bit-identical
                                 outputs (BN statistics aside: atomics); callers may time them. */
   /* epilogue */
   const float* bias;         /* [cout] or NULL */
@@ -92,9 +93,16 @@ typedef struct {
   const void* bwd_raw;       /* NULL = off (then stat_sum / stat_sqsum are the forward statistics above) */
   const float* bwd_coef;
   int32_t bwd_relu;
+  /* Split-K (bits 25-27 of algo = 2 or 4): for maps with fewer 128-pixel tiles than SMs the reduction over the input
+   * channels is split across CTAs; the fp32 partial tiles go to `workspace` (caller-owned, gdn_conv2d_workspace_bytes(d)
+   * bytes, private to the stream) and a second kernel on the same stream sums them in a fixed order and applies the
+   * epilogue above.  Plain destinations only (no strides, border, reflection, tanh; cout a power of two). */
+  void* workspace;
+  size_t workspace_bytes;
 } gdn_conv_desc;
 
 int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream);
+size_t gdn_conv2d_workspace_bytes(const gdn_conv_desc* d);   /* 0 unless the algo word asks for split-K */
 
 /* Weight gradient: dw[tap][ci][co] (fp32, += ) = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride + r + off_y, ox*stride + s + off_x, ci] */
 typedef struct {

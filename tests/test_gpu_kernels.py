@@ -76,6 +76,13 @@ def _conv_case(N, H, W, cin, cout, k, stride=1, reflect=False, algo=0, relu=Fals
     ssum = torch.zeros((2, cout), dtype=torch.float64, device=dev)
     if stats:
         d.stat_sum, d.stat_sqsum = ssum[0].data_ptr(), ssum[1].data_ptr()
+    if (algo >> 25) & 7:       # split-K: caller-owned workspace, sized by the library
+        need = _lib.lib().gdn_conv2d_workspace_bytes(C.byref(d))
+        assert need == ((algo >> 25) & 7) * N * OH * OW * cout * 4
+        assert _lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()) == -3      # refused without it
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), need
+        keep.append(ws)
     _lib.check(_lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
@@ -118,6 +125,14 @@ CONV_CASES = [
     dict(N=2, H=32, W=64, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24)),
     dict(N=3, H=16, W=40, cin=256, cout=512, k=3, stride=2, algo=1 | (1 << 24), stats=True),
     dict(N=3, H=16, W=40, cin=128, cout=64, k=1, algo=1 | (1 << 24), cin2=128, stats=True),
+    # split-K (algo bits 25-27) on the small 512-channel maps: every epilogue operator goes through the combine kernel
+    dict(N=5, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24) | (2 << 25), relu=True, bias=True, resid=True, stats=True),
+    dict(N=3, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (4 << 25), stats=True),
+    dict(N=2, H=16, W=52, cin=512, cout=512, k=3, algo=2 | (1 << 8) | (1 << 24) | (2 << 25), stats=True),
+    dict(N=3, H=8, W=26, cin=256, cout=256, k=1, algo=1 | (2 << 25), cin2=256, relu=True, bias=True),
+    dict(N=20, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24) | (2 << 25), stats=True, f32ref=True),
+    dict(N=20, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (2 << 16) | (1 << 24) | (4 << 25), relu=True, bias=True, resid=True,
+         f32ref=True),
     # the bench configuration itself (B = 20, 128 x 416 and its coarser maps): the persistent loop over 8 320 pixel tiles,
     # stage-ring wrap-around, the odd CTA-pair tail, and the shipped variants (pairs, J = 4 / 2 / 1)
     dict(N=20, H=128, W=416, cin=64, cout=64, k=9, algo=2 | (4 << 8) | (1 << 24), stats=True, f32ref=True),

@@ -191,7 +191,9 @@ def test_fp32_only_epilogue_strided_destination(cin, cout, k, stride2dst, resid,
     (128, 64, 1, True, True, False, 0, 2, 24, 40),
     (64, 128, 3, False, True, True, 2 | (2 << 8), 3, 16, 24),
     (512, 512, 3, True, False, False, 1 | (1 << 24), 4, 8, 26),
-    (64, 64, 9, True, True, False, 2 | (4 << 8) | (1 << 24), 4, 64, 96)])
+    (64, 64, 9, True, True, False, 2 | (4 << 8) | (1 << 24), 4, 64, 96),
+    (512, 512, 3, True, True, True, 1 | (1 << 24) | (2 << 25), 4, 8, 26),         # split-K: the combine kernel does it
+    (512, 512, 3, False, False, False, 1 | (4 << 25), 3, 8, 26)])
 def test_fused_bn_backward_statistics_epilogue(cin, cout, k, relu, resid, keep32, algo, N, H, W):
     """gdn_conv_desc.bwd_raw: the input-gradient launch that completes a tensor's gradient applies the producer's ReLU mask
     and reduces sum g / sum g*xhat in its epilogue.  Against the separate path: fp64 conv (+ accumulate), mask from the
@@ -234,6 +236,9 @@ def test_fused_bn_backward_statistics_epilogue(cin, cout, k, relu, resid, keep32
     d.out_f32 = out32.data_ptr() if keep32 else None
     d.bwd_raw, d.bwd_coef, d.bwd_relu = raw.data_ptr(), coef.data_ptr(), int(relu)
     d.stat_sum, d.stat_sqsum = sums[0].data_ptr(), sums[1].data_ptr()
+    if (algo >> 25) & 7:
+        ws = torch.empty(_lib.lib().gdn_conv2d_workspace_bytes(C.byref(d)), dtype=torch.uint8, device=dev)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     _lib.check(_lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv")
     torch.cuda.synchronize()
     scale_ = tot.abs().max().item()
