@@ -105,7 +105,7 @@ def build_models(dev, h=H, w=W):
     return rtod.to(dev), dtod.to(dev).eval()
 
 
-def time_dominant_conv(dev, B):
+def time_dominant_conv(dev, B, profile_launches=0):
     """64->64 k9 same conv on (B,128,416): the kernel that dominates the step, timed alone with CUDA events"""
     import ctypes as C
     from gdn_pytorch_b200 import _lib
@@ -139,6 +139,12 @@ def time_dominant_conv(dev, B):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * H * W * 64 * 64 * 81
+    if profile_launches:            # tools/profile_conv.py under `ncu --profile-from-start off`: the shipped variant only
+        torch.cuda.profiler.start()
+        for _ in range(profile_launches):
+            L.gdn_conv2d(C.byref(d), _lib.stream_ptr())
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     return ms, flops, algo
 
 

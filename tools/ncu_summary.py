@@ -23,7 +23,20 @@ KEYS = [
 ]
 
 
-def main(path):
+def _num(v):
+    try:
+        return float(v.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def _scaled(v, unit):
+    """ncu prints durations / bytes in the unit it likes: bring them to seconds / bytes"""
+    f = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit)
+    return None if (v is None or f is None) else v * f
+
+
+def main(path, traffic_json=None, match=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -40,8 +53,21 @@ def main(path):
                 except ValueError:
                     pass
                 parts.append("%s=%s%s" % (short, v, ("" if u in ("%", "") else " " + u)))
+        g = lambda kname: _scaled(_num(r[col[kname]]), units[col[kname]]) if kname in col else None
+        t, rd, wr = g("gpu__time_duration.sum"), g("dram__bytes_read.sum"), g("dram__bytes_write.sum")
+        if t and rd is not None and wr is not None:
+            parts.append("dram=%.0f GB/s (%.3f of the measured 6555.8)" % ((rd + wr) / t / 1e9, (rd + wr) / t / 1e9 / 6555.8))
         print("  ".join(parts))
+        if traffic_json and (match is None or match in name) and rd is not None:
+            import json
+            json.dump({"kernel": name, "dram_bytes_read": rd, "dram_bytes_write": wr, "time_s": t,
+                       "source": "ncu --set full --clock-control none, %s (one launch of the shipped variant, B = 20)" % path},
+                      open(traffic_json, "w"), indent=1)
+            traffic_json = None
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    # python tools/ncu_summary.py x.ncu-rep [--traffic-json profiles/dominant_conv_traffic.json [kernel-name-substring]]
+    tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
+    mt = sys.argv[sys.argv.index("--traffic-json") + 2] if tj and len(sys.argv) > sys.argv.index("--traffic-json") + 2 else None
+    main(sys.argv[1], tj, mt)
