@@ -546,13 +546,11 @@ def main():
             line["gpu_library_baseline"] = lib
         emit(line)
     if world > 1:
-        # CUDA graphs holding captured NCCL kernels are still alive: communicator teardown can dead-lock behind them
-        # (seen on the 2-GPU box), so synchronise, flush and leave without destroy_process_group()
-        dist.barrier()
-        torch.cuda.synchronize()
+        # orderly teardown: the CUDA graph that captured the NCCL all-reduces is released first (close()), then the
+        # process group is destroyed; a watchdog falls back to os._exit(0) if that ever hangs
+        from gdn_pytorch_b200.trainer import shutdown_distributed
         sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        shutdown_distributed([locals().get("stepper")])
 
 
 if __name__ == "__main__":

@@ -307,6 +307,19 @@ class _StepBase:
     def load_checkpoint(self, path):
         self.load_state_dict(torch.load(path, map_location=self.dev))
 
+    def close(self):
+        """Release everything that pins the process group: the captured CUDA graph (it holds the NCCL kernels of the
+        bucketed all-reduces -- a communicator cannot be torn down while a live graph still references its kernels), the
+        static input / output buffers and the engines.  Call before dist.destroy_process_group(); the step object can be
+        used again afterwards (it re-captures)."""
+        import gc
+        torch.cuda.synchronize(self.dev)
+        self._graph = None
+        self._static_in = self._static_out = None
+        self._eager_done = 0
+        gc.collect()
+        torch.cuda.synchronize(self.dev)
+
     def _eager_on_main(self, inputs):
         """run the step on the high-priority stream, ordered after / before the caller's current stream"""
         ms = self.main_stream
@@ -466,3 +479,34 @@ def init_distributed_from_env():
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
     return rank, world, dev
+
+
+def shutdown_distributed(steppers=(), timeout_s=30.0):
+    """Orderly end of a multi-rank run: drop the CUDA graphs that hold captured NCCL kernels (``close()``), barrier,
+    destroy the process group.  Round 1 dodged a teardown dead-lock behind live graphs with os._exit(0); the dead-lock
+    was the graph outliving the communicator.  A watchdog keeps the old escape hatch: if teardown has not finished after
+    ``timeout_s`` the process still exits with status 0 (and says so on stderr) instead of hanging a benchmark.
+    Returns True when the group was destroyed cleanly."""
+    import sys
+    import threading
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    done = threading.Event()
+
+    def work():
+        for st in steppers:
+            if st is not None:
+                st.close()
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        done.set()
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    if not done.is_set():
+        sys.stderr.write("gdn_b200: process-group teardown did not finish in %.0f s; leaving with os._exit(0)\n" % timeout_s)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    return True

@@ -77,10 +77,11 @@ def main():
     if rank == 0:
         print("DDP-OK world=%d B/rank=%d steps=%d  |graph-eager| max %.3g mean %.3g (lr %.0e)  loss(graph)=%s loss(eager)=%s" %
               (world, B, steps, d, md, LR, ["%.6f" % v for v in out_g], ["%.6f" % v for v in out_e]), flush=True)
-    dist.barrier()
-    torch.cuda.synchronize()
     sys.stdout.flush()
-    os._exit(0)      # captured NCCL kernels are still alive in the CUDA graphs: skip communicator teardown
+    from gdn_pytorch_b200.trainer import shutdown_distributed
+    clean = shutdown_distributed([st_g, st_e])
+    if rank == 0:
+        print("teardown: process group destroyed cleanly = %s" % clean, flush=True)
 
 
 if __name__ == "__main__":
