@@ -119,53 +119,6 @@ __global__ void im2col_kernel(const float* __restrict__ src, __nv_bfloat16* __re
 }
 
 
-// fast path: one image row per CTA iteration; the (r, s, c) decomposition of every column lives in a shared-memory
-// table, all index math is 32-bit.
-__global__ void __launch_bounds__(kEwThreads) im2col_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                                 int N, int C, int H, int W, int kh, int kw, int pad,
-                                                                 int reflect, int kpad) {
-  extern __shared__ int s_tab[];  // [kpad]: r | s << 8 | c << 16, or -1 beyond kh*kw*C
-  const int kreal = kh * kw * C;
-  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
-    int e = -1;
-    if (k < kreal) {
-      const int c = k % C, t = k / C;
-      e = (t / kw) | ((t % kw) << 8) | (c << 16);
-    }
-    s_tab[k] = e;
-  }
-  __syncthreads();
-  const int groups = kpad >> 3;
-  const int items = W * groups;
-  const int rows = N * H;
-  const int plane = H * W;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / H, y = row - n * H;
-    const float* img = src + (size_t)n * C * plane;
-    for (int it = threadIdx.x; it < items; it += kEwThreads) {
-      const int x = it / groups, g = it - x * groups;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int e = s_tab[g * 8 + j];
-        float v = 0.f;
-        if (e >= 0) {
-          int yy = y + (e & 255) - pad, xx = x + ((e >> 8) & 255) - pad;
-          bool ok = true;
-          if (reflect) {
-            yy = reflect_idx(yy, H);
-            xx = reflect_idx(xx, W);
-          } else {
-            ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
-          }
-          if (ok) v = __ldg(img + (e >> 16) * plane + yy * W + xx);
-        }
-        f[j] = v;
-      }
-      *reinterpret_cast<uint4*>(dst + ((size_t)row * W + x) * kpad + g * 8) = pack8(f);
-    }
-  }
-}
 
 // shared-memory path (the one the networks use): the kh input rows an output row needs are staged ONCE per output row
 // in shared memory, pixel-interleaved ([row][x + pad][c], borders already reflected / zeroed), so that the kw*C columns
@@ -530,6 +483,76 @@ __global__ void __launch_bounds__(kEwThreads, 3) act_up_rows_kernel(const ActFwd
         v[j] = (1.f - wy) * top + wy * bot;
       }
       *reinterpret_cast<uint4*>(a.out_bf16 + ((size_t)row * Wp + xp) * a.C + c8) = pack8(v);
+    }
+  }
+}
+
+// Pure x2 bilinear upsampling (align_corners=False) of a plain bf16 tensor into a (reflection-)bordered bf16 buffer --
+// the operand of the decoder's up-convolutions (F.interpolate + nn.ReflectionPad2d, AE_model_unet.py:336-355, 66).
+// SOURCE-block driven: a thread owns the 2 x 2 source block (yb, yb+1) x (xb, xb+1) of 8 channels and produces the
+// 2 x 2 outputs (2yb+1, 2yb+2) x (2xb+1, 2xb+2) it alone determines (fixed weights 0.75 / 0.25; yb = -1 and H-1 give the
+// clamped edge rows), plus their reflection images: four 16-byte loads for four 16-byte stores.  The output-driven
+// act_up_rows_kernel re-reads four sources and redoes the coordinate arithmetic per OUTPUT (1.4 TB/s at the bench
+// shapes, profiles/r02e_ncu_elem.summary.txt); it stays for the fused BatchNorm / residual / fp32-source forms.
+__global__ void __launch_bounds__(kEwThreads, 3) up2x_blocks_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  const int cgm = (1 << lg_cg) - 1;
+  const int OH = 2 * a.H, OW = 2 * a.W;
+  const int P = a.P, Hp = OH + 2 * P, Wp = OW + 2 * P;
+  const int items = (a.W + 1) << lg_cg;
+  const int c8 = (threadIdx.x & cgm) * 8;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {      // row = (image, source-block row yb + 1)
+    const int n = row / (a.H + 1), yb = row - n * (a.H + 1) - 1;
+    const int y0 = max(yb, 0), y1 = min(yb + 1, a.H - 1);
+    const size_t base0 = ((size_t)n * a.H + y0) * a.W, base1 = ((size_t)n * a.H + y1) * a.W;
+    // the two output rows of this block row and the buffer rows holding them (interior + reflection images)
+    int ys[2][3], ny[2] = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int Y = 2 * yb + 1 + r;
+      if (Y < 0 || Y >= OH) continue;
+      ys[r][ny[r]++] = Y + P;
+      if (a.reflect) {
+        if (Y >= 1 && Y <= P) ys[r][ny[r]++] = P - Y;
+        if (Y >= OH - 1 - P && Y <= OH - 2) ys[r][ny[r]++] = P + 2 * (OH - 1) - Y;
+      }
+    }
+    for (int it = threadIdx.x; it < items; it += kEwThreads) {
+      const int xb = (it >> lg_cg) - 1;
+      const int x0 = max(xb, 0), x1 = min(xb + 1, a.W - 1);
+      float v00[8], v01[8], v10[8], v11[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.src_bf16 + (base0 + x0) * a.C + c8)), v00);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.src_bf16 + (base0 + x1) * a.C + c8)), v01);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.src_bf16 + (base1 + x0) * a.C + c8)), v10);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.src_bf16 + (base1 + x1) * a.C + c8)), v11);
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int X = 2 * xb + 1 + c;
+        if (X < 0 || X >= OW) continue;
+        // same expression as the output-driven kernel: weight of the second source = 0.25 for odd outputs, 0.75 for even ones
+        const float wx = (x0 == x1) ? 0.f : (c ? 0.75f : 0.25f);     // clamped edge columns copy their source exactly
+        int xs[3], nx = 0;
+        xs[nx++] = X + P;
+        if (a.reflect) {
+          if (X >= 1 && X <= P) xs[nx++] = P - X;
+          if (X >= OW - 1 - P && X <= OW - 2) xs[nx++] = P + 2 * (OW - 1) - X;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (ny[r] == 0) continue;
+          const float wy = (y0 == y1) ? 0.f : (r ? 0.75f : 0.25f);
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float top = (1.f - wx) * v00[j] + wx * v01[j];
+            const float bot = (1.f - wx) * v10[j] + wx * v11[j];
+            v[j] = (1.f - wy) * top + wy * bot;
+          }
+          const uint4 o = pack8(v);
+          for (int p = 0; p < ny[r]; p++)
+            for (int q = 0; q < nx; q++)
+              *reinterpret_cast<uint4*>(a.out_bf16 + (((size_t)n * Hp + ys[r][p]) * Wp + xs[q]) * a.C + c8) = o;
+        }
+      }
     }
   }
 }
@@ -989,40 +1012,6 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
 constexpr int kPackTile = 16;
 constexpr int kPackMaxTaps = 81;
 
-__device__ __forceinline__ void pack_tile_body(const float* __restrict__ w, const float* __restrict__ scale_a,
-                                               __nv_bfloat16* __restrict__ out, const PackK& k, const int a0, const int b0,
-                                               float* s_tile) {
-  // tile[a_local][b_local][tap]; parameter address of (a, b, tap) = a*sa + b*sb + tap  (one of sa / sb is T = taps)
-  const int T = k.kh * k.kw;
-  const bool b_inner = (k.sb == T);  // [a][b][taps] (Conv2d)  vs  [b][a][taps] (ConvTranspose2d / dgrad views)
-  const int run = kPackTile * T;     // contiguous floats per outer index
-  for (int i = threadIdx.x; i < kPackTile * run; i += blockDim.x) {
-    const int outer = i / run, rem = i - outer * run;
-    const int inner = rem / T, tap = rem - inner * T;
-    const int al = b_inner ? outer : inner, bl = b_inner ? inner : outer;
-    const int a = a0 + al, b = b0 + bl;
-    float v = 0.f;
-    if (a < k.A && b < k.B) v = __ldg(w + (long long)a * k.sa + (long long)b * k.sb + tap);
-    s_tile[(al * kPackTile + bl) * (T + 1) + tap] = v;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * kPackTile * kPackTile; i += blockDim.x) {
-    const int bl = i & (kPackTile - 1), al = (i >> 4) & (kPackTile - 1), t = i >> 8;
-    const int a = a0 + al, b = b0 + bl;
-    if (a >= k.Apad || b >= k.Bpad) continue;
-    const int tap = k.flip ? T - 1 - t : t;
-    float v = s_tile[(al * kPackTile + bl) * (T + 1) + tap];
-    if (scale_a && a < k.A) v *= scale_a[a];
-    out[((long long)t * k.Apad + a) * k.Bpad + b] = __float2bfloat16(v);
-  }
-}
-
-__global__ void __launch_bounds__(256) pack_tile_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
-                                                       __nv_bfloat16* __restrict__ out, const PackK k) {
-  extern __shared__ float s_tile[];
-  pack_tile_body(w, scale_a, out, k, blockIdx.y * kPackTile, blockIdx.x * kPackTile, s_tile);
-}
-
 // All weight packs of a network in ONE launch: a device table of jobs (one per packed tensor), CTA c works on tile
 // (c - cta0) of the job whose [cta0, cta0 + tiles) range contains it.  A training step re-packs ~90 tensors; as
 // separate launches they are latency-bound (~16 us each), as one launch the whole re-pack is a single HBM-bound pass.
@@ -1032,7 +1021,7 @@ struct PackJob {
   const float* scale_a;
   __nv_bfloat16* out;
   int cta0, tiles_x;
-  int tb;            // b-tile width of the wide-tile version (pack_tile.cuh); 0 = first version (16 x 16 tiles)
+  int tb;            // b-tile width (pack_tile.cuh: 16 x 64 / 32 / 16 tiles by tap count)
 };
 
 __global__ void __launch_bounds__(256) pack_tile2_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
@@ -1057,14 +1046,10 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restri
   }
   __syncthreads();
   const int tile = blockIdx.x - job.cta0;
-  if (job.tb > 0) {
-    const int a0 = (tile / job.tiles_x) * kPackTA, b0 = (tile % job.tiles_x) * job.tb;
-    pack_v2_phase1(job.w, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
-    __syncthreads();
-    pack_v2_phase2(job.scale_a, job.out, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
-    return;
-  }
-  pack_tile_body(job.w, job.scale_a, job.out, job.k, (tile / job.tiles_x) * kPackTile, (tile % job.tiles_x) * kPackTile, s_tile);
+  const int a0 = (tile / job.tiles_x) * kPackTA, b0 = (tile % job.tiles_x) * job.tb;
+  pack_v2_phase1(job.w, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
+  __syncthreads();
+  pack_v2_phase2(job.scale_a, job.out, job.k, a0, b0, job.tb, s_tile, threadIdx.x, blockDim.x);
 }
 
 // grad[a*sa + b*sb + tap] (+)= dw[t][b][a]
@@ -1094,12 +1079,6 @@ __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restric
     const float v = s_tile[(al * kPackTile + bl) * (T + 1) + tap];
     if (accumulate) *g += v; else *g = v;
   }
-}
-
-static bool pack_v1() {   // GDN_PACK_V1=1: the first version of the tile kernels (16 x 16 tiles), A/B knob
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GDN_PACK_V1"); v = (e && atoi(e) == 1) ? 1 : 0; }
-  return v == 1;
 }
 
 static bool pack_tileable(const PackK& k) {
@@ -1146,12 +1125,6 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
       GDN_LAUNCH_CHECK("im2col_smem_kernel");
       return GDN_OK;
     }
-  }
-  if (kh < 256 && kw < 256 && (long long)h * w * c < (1ll << 31)) {
-    im2col_rows_kernel<<<ew_row_grid((long long)n * h), kEwThreads, kpad * sizeof(int), (cudaStream_t)stream>>>(
-        src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad);
-    GDN_LAUNCH_CHECK("im2col_rows_kernel");
-    return GDN_OK;
   }
   const long long work = (long long)n * h * w * (kpad / 8);
   im2col_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad,
@@ -1214,9 +1187,17 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
       GDN_LAUNCH_CHECK("act_rows_kernel");
     }
     if (a.up && a.out_bf16) {
-      const int rows = a.N * (OH + 2 * a.P);
-      act_up_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
-      GDN_LAUNCH_CHECK("act_up_rows_kernel");
+      const bool pure = a.src_bf16 && !a.src_half && !a.scale && !a.resid && !a.relu && !a.out_f32 && a.H >= 2 && a.W >= 2 &&
+                        a.P < 2 * a.H && a.P < 2 * a.W;
+      if (pure) {
+        const int rows = a.N * (a.H + 1);
+        up2x_blocks_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
+        GDN_LAUNCH_CHECK("up2x_blocks_kernel");
+      } else {
+        const int rows = a.N * (OH + 2 * a.P);
+        act_up_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
+        GDN_LAUNCH_CHECK("act_up_rows_kernel");
+      }
     }
     return GDN_OK;
   }
@@ -1364,30 +1345,17 @@ GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float
   fill_pack(d, k);
   if (pack_tileable(k)) {
     const int T = k.kh * k.kw;
-    const size_t smem = (size_t)kPackTile * kPackTile * (T + 1) * sizeof(float);
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-      GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      GDN_CUDA_CHECK(cudaFuncSetAttribute(unpack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured[dev] = true;
     }
-    if (!pack_v1()) {
-      static bool configured2[64] = {false};
-      if (dev >= 0 && dev < 64 && !configured2[dev]) {
-        GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured2[dev] = true;
-      }
-      const int tb = pack_tb_for_taps(T);
-      dim3 grid2((k.Bpad + tb - 1) / tb, (k.Apad + kPackTA - 1) / kPackTA);
-      pack_tile2_kernel<<<grid2, 256, pack_smem_bytes(T), (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k, tb);
-      GDN_LAUNCH_CHECK("pack_tile2_kernel");
-      return GDN_OK;
-    }
-    dim3 grid((k.Bpad + kPackTile - 1) / kPackTile, (k.Apad + kPackTile - 1) / kPackTile);
-    pack_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
-    GDN_LAUNCH_CHECK("pack_tile_kernel");
+    const int tb = pack_tb_for_taps(T);
+    dim3 grid2((k.Bpad + tb - 1) / tb, (k.Apad + kPackTA - 1) / kPackTA);
+    pack_tile2_kernel<<<grid2, 256, pack_smem_bytes(T), (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k, tb);
+    GDN_LAUNCH_CHECK("pack_tile2_kernel");
     return GDN_OK;
   }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.Apad * k.Bpad;
@@ -1412,15 +1380,9 @@ GDN_API int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const floa
   j.scale_a = scale_a;
   j.out = (__nv_bfloat16*)out;
   j.cta0 = cta0;
-  if (pack_v1()) {
-    j.tb = 0;
-    j.tiles_x = (j.k.Bpad + kPackTile - 1) / kPackTile;
-    *n_ctas = j.tiles_x * ((j.k.Apad + kPackTile - 1) / kPackTile);
-  } else {
-    j.tb = pack_tb_for_taps(j.k.kh * j.k.kw);
-    j.tiles_x = (j.k.Bpad + j.tb - 1) / j.tb;
-    *n_ctas = j.tiles_x * ((j.k.Apad + kPackTA - 1) / kPackTA);
-  }
+  j.tb = pack_tb_for_taps(j.k.kh * j.k.kw);
+  j.tiles_x = (j.k.Bpad + j.tb - 1) / j.tb;
+  *n_ctas = j.tiles_x * ((j.k.Apad + kPackTA - 1) / kPackTA);
   memcpy(job_out, &j, sizeof(j));
   return GDN_OK;
 }
@@ -1429,12 +1391,10 @@ GDN_API int gdn_pack_job_fill(const gdn_pack_desc* d, const float* w, const floa
 GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ctas, int max_taps, gdn_stream stream) {
   if (!jobs_dev || njobs <= 0 || total_ctas <= 0 || max_taps <= 0 || max_taps > kPackMaxTaps)
     return fail(GDN_INVALID_DESC, "gdn_pack_weights_table: bad arguments");
-  // every job of one table has max_taps taps (the caller groups by kernel size); the wide-tile version sizes its tile
-  // by the tap count, the first version is 16 x 16 x (taps + 1)
-  size_t smem = (size_t)kPackTile * kPackTile * (max_taps + 1) * sizeof(float);
-  if (!pack_v1())
-    for (int t = 1; t <= max_taps; t++)      // a table may mix tap counts <= max_taps; the tile size is not monotonic in t
-      if (pack_smem_bytes(t) > smem) smem = pack_smem_bytes(t);
+  // every job of one table has max_taps taps (the caller groups by kernel size); the tile is sized by the tap count
+  size_t smem = 0;
+  for (int t = 1; t <= max_taps; t++)      // a table may mix tap counts <= max_taps; the tile size is not monotonic in t
+    if (pack_smem_bytes(t) > smem) smem = pack_smem_bytes(t);
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1458,7 +1418,6 @@ GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* gra
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-      GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       GDN_CUDA_CHECK(cudaFuncSetAttribute(unpack_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       configured[dev] = true;
     }

@@ -112,6 +112,14 @@ class LossKernels:
         """mode 0 = RtoD (BerHu + edge-aware smoothness), 1 = DtoD (BerHu + 3*Sobel).  absdiff_max() (and, when the
         batch is sharded, an all-reduce MAX of self.maxabs) must have run before."""
         N, H, W = out.shape[0], out.shape[-2], out.shape[-1]
+        # the kernel indexes every operand with the prediction's extents: a mismatched tensor would be read out of bounds
+        for name, t, chans in (("gt", gt, (1,)), ("sparse", sparse, (1, 3)), ("rgb", rgb, (3,)), ("dout", dout, (1,)),
+                               ("dpre", dpre, (1,))):
+            if t is None:
+                continue
+            if t.shape[0] != N or t.shape[-2:] != out.shape[-2:] or t.numel() // (N * H * W) not in chans or not t.is_contiguous():
+                raise ValueError("gdn_b200 loss: %s has shape %s, expected (%d, %s, %d, %d) contiguous"
+                                 % (name, tuple(t.shape), N, "|".join(map(str, chans)), H, W))
         d = LossDesc()
         d.out, d.gt = out.data_ptr(), gt.data_ptr()
         if sparse is not None:

@@ -43,6 +43,12 @@ ACT_CASES = [
     (2, 8, 12, 64, "f32", False, False, False, False, True, 3, 1, 2, 0),
     (20, 128, 416, 64, "half", True, True, False, False, True, 0, 0, 0, 0),
     (4, 64, 208, 128, "half", True, False, True, True, True, 3, 1, 1, 0),
+    # pure x2 bilinear of a plain bf16 tensor (+ reflection border): the source-block-driven kernel (up2x_blocks_kernel)
+    (2, 8, 26, 512, "bf16", False, False, False, False, True, 1, 1, 1, 0),
+    (3, 9, 7, 64, "bf16", False, False, False, False, True, 3, 1, 1, 0),
+    (2, 6, 10, 128, "bf16", False, False, False, False, True, 0, 0, 1, 0),
+    (2, 5, 6, 64, "bf16", False, False, False, False, True, 2, 0, 1, 0),
+    (20, 64, 208, 128, "bf16", False, False, False, False, True, 3, 1, 1, 0),
 ]
 
 

@@ -12,7 +12,8 @@ def main(path):
     rows = list(csv.reader(open(path)))
     start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     ci = {h: i for i, h in enumerate(rows[start])}
-    L = [(r[ci["Kernel Name"]], float(r[ci["Metric Value"]].replace(",", ""))) for r in rows[start + 1:] if len(r) > ci["Metric Value"]]
+    L = [(r[ci["Kernel Name"]], float(r[ci["Metric Value"]].replace(",", ""))) for r in rows[start + 1:]
+         if len(r) > ci["Metric Value"] and r[ci["Metric Name"]] == "gpu__time_duration.sum"]
     ends = [i for i, (n, _) in enumerate(L) if "adam_kernel" in n]
     if len(ends) >= 2:
         L = L[ends[-2] + 1: ends[-1] + 1]

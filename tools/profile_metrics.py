@@ -49,10 +49,10 @@ algo = 28.0 * b * h * w
 print("absdiff_max + loss(RtoD) B=%d %dx%d: %.4f ms  algorithmic 28 B/pixel (+8 for the max pass) = %.2f MB -> %.1f GB/s"
       % (b, h, w, ms, algo / 1e6, (algo + 8.0 * b * h * w) / ms / 1e6))
 torch.cuda.profiler.start()
-for (b, h, w) in ((8, 128, 416), (8, 384, 1248)):
-    rgb, dep, spa = [t.to(dev) for t in bench.synth_batch(b, 0, h, w)]
-    pred = torch.tanh(torch.randn((b, 1, h, w), device=dev))
-    ops.eigen_metrics_device(spa, dep, pred, crop=True)
+for (b2, h2, w2) in ((8, 128, 416), (8, 384, 1248)):
+    _, dep2, spa2 = [t.to(dev) for t in bench.synth_batch(b2, 0, h2, w2)]
+    pred2 = torch.tanh(torch.randn((b2, 1, h2, w2), device=dev))
+    ops.eigen_metrics_device(spa2, dep2, pred2, crop=True)
 loss()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
