@@ -1171,22 +1171,16 @@ class Engine:
             self.algo_choice[what] = d.algo
 
     def profile(self, ops, reps=3, with_flops=False):
-        """per-op device time (CUDA events, ms) of a list of ops (self.fwd or self.bwd); development aid.
+        """per-op device time (ms; each op captured in a CUDA graph and replayed) of a list of ops (self.fwd or self.bwd).
         with_flops: rows are (label, ms, flops or None, 128-pixel tiles or None)"""
-        s = _lib.stream_ptr()
-        evs = []
+        res = []
         for op in ops:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                op(s)
-            e1.record()
-            evs.append((getattr(op, "label", "misc"), e0, e1))
-        torch.cuda.synchronize()
-        if with_flops:
-            return [(n, a.elapsed_time(b) / reps, getattr(op, "flops", None), getattr(op, "tiles", None))
-                    for (n, a, b), op in zip(evs, ops)]
-        return [(n, a.elapsed_time(b) / reps) for n, a, b in evs]
+            ms = graph_time_ms(op, reps)       # graph-captured: eager timing of the small ops measures the host
+            if with_flops:
+                res.append((getattr(op, "label", "misc"), ms, getattr(op, "flops", None), getattr(op, "tiles", None)))
+            else:
+                res.append((getattr(op, "label", "misc"), ms))
+        return res
 
     def backward(self, dpre=None, dout_nhwc=None):
         """dpre: dL/d(pre-tanh output), fp32 (N, H, W) -- or None if the loss kernel already wrote self.dpre.
@@ -1273,14 +1267,33 @@ def autotune_conv(L, d, reps=3, what="conv"):
                 torch.cuda.synchronize()
             except Exception as e:
                 raise RuntimeError("gdn_b200: kernel failure autotuning '%s' with algo 0x%x: %s" % (what, algo, e))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn(C.byref(d), s)
-        e1.record()
-        e1.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = graph_time_ms(lambda sp: fn(C.byref(d), sp), reps)
         if best_ms is None or ms < best_ms:
             best, best_ms = algo, ms
     d.algo = best
+    return best
+
+
+def graph_time_ms(launch, reps=3, inner=6):
+    """device time of ``inner`` back-to-back launches, captured in a CUDA graph and replayed ``reps`` times (ms per launch,
+    best replay).  Eager timing of small kernels measures the HOST: one gdn_conv2d call costs ~40 us of Python / ctypes /
+    tensor-map encoding, more than the kernel itself on the 8x26 and 16x52 maps -- the round-1 autotuner and the round-2
+    variant sweeps (profiles/r02b_sweep_conv.log: every variant of the small layers at the same ~47 us) were blind there."""
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        sp = _lib.stream_ptr()
+        for _ in range(inner):
+            launch(sp)
+    g.replay()                               # warm-up replay (graph upload)
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / inner
+        best = ms if best is None else min(best, ms)
+    del g
     return best
