@@ -56,6 +56,7 @@ def lib():
         L.gdn_sm_count.restype = C.c_int
         L.gdn_resize_u8_workspace.restype = C.c_size_t
         L.gdn_conv2d_workspace_bytes.restype = C.c_size_t
+        L.gdn_depth_metrics_workspace_bytes.restype = C.c_size_t
         _lib = L
     return _lib
 

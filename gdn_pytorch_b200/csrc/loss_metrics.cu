@@ -244,7 +244,7 @@ __global__ void tanh_chain_add_kernel(const float* __restrict__ dout, const floa
 }
 
 // ---------------------------------------------------------------------------------------- depth metrics
-// One block per image.  Arithmetic follows calculate_error.py operation by operation in fp32.
+// Arithmetic follows calculate_error.py operation by operation in fp32.
 //   VAR 0  compute_errors        (KITTI / Eigen, :10-103)   out8 = abs_diff abs_rel sq_rel a1 a2 a3 rmse rmse_log
 //   VAR 1  compute_errors_NYU    (:105-151)                 out8 = abs_diff abs_rel log10  a1 a2 a3 rmse rmse_log
 //   VAR 2  compute_errors_Make3D (:153-182)                 out8 = abs_diff abs_rel log10  -  -  -  rmse -
@@ -297,59 +297,47 @@ __device__ __forceinline__ bool metric_pixel(const MetricK& m, const MinMax& mm,
   return valid;
 }
 
-// k-th smallest (0-based) of the valid values via 4-pass radix select on the (non-negative) float bit patterns
-template <int VAR, bool PRED>
-__device__ float select_kth(const MetricK& m, const MinMax& mm, const float* __restrict__ gtn, const float* __restrict__ g,
-                            const float* __restrict__ p, long long kth, unsigned int* hist /* [256] smem */,
-                            unsigned int* s_prefix, long long* s_k) {
-  const int HW = m.H * m.W;
-  unsigned int prefix = 0, mask = 0;
-  long long k = kth;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      float vg, vp;
-      if (!metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) continue;
-      const unsigned int bits = __float_as_uint(PRED ? vp : vg);
-      if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      long long kk = k;
-      unsigned int b = 0;
-      for (; b < 256; b++) {
-        if (kk < (long long)hist[b]) break;
-        kk -= hist[b];
-      }
-      *s_prefix = prefix | (b << shift);
-      *s_k = kk;
-    }
-    __syncthreads();
-    prefix = *s_prefix;
-    k = *s_k;
-    mask |= (255u << shift);
-    __syncthreads();
+// ---- staged evaluation: many CTAs per image, per-image state in a caller-owned workspace -------------------------
+// Round 1 ran ONE 1024-thread CTA per image through 11 passes (min/max, count, 2 x 4 radix passes, metrics): 0.43 ms
+// for 8 images of 128x416 and 3.8 ms at 384x1248 on 8 of 148 SMs (profiles/r02e_ncu_metrics.summary.txt: 12 GB/s).
+// Now: 6 launches over (chunks, images) grids -- min/max; four radix passes that histogram the ground-truth AND the
+// prediction values at once (the valid count is the total of the first histogram); the metric sums, finished by the last
+// CTA of each image.  The per-pixel arithmetic (metric_pixel) is unchanged, medians are still exact radix selects and
+// the delta-threshold counts integer-valued sums, so the COUNTS stay bit-exact; the fp64 sums are accumulated with
+// atomics (order-dependent in the last bits only).
+struct MetricImg {            // per image, zeroed by the host wrapper before the first kernel
+  unsigned int mm[6];         // order-preserving encodings of gmin gmax pmin pmax nmin nmax (atomicMin / atomicMax)
+  unsigned int done;          // CTAs of the final pass that have contributed
+  unsigned int pad;
+  unsigned int hist[4][2][256];   // [radix pass][0 = gt, 1 = pred][bin]
+  double sums[9];
+};
+
+__device__ __forceinline__ unsigned int m_f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float m_ord2f(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void metrics_init_kernel(MetricImg* ws, int B) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * (int)(sizeof(MetricImg) / 4); i += gridDim.x * blockDim.x) {
+    const int img = i / (int)(sizeof(MetricImg) / 4), w = i - img * (int)(sizeof(MetricImg) / 4);
+    unsigned int v = 0u;
+    if (w < 6) v = (w & 1) ? 0u : 0xffffffffu;            // running max starts at the smallest encoding, min at the largest
+    reinterpret_cast<unsigned int*>(ws + img)[w] = v;
   }
-  return __uint_as_float(prefix);
 }
 
 template <int VAR>
-__global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m) {
-  const int b = blockIdx.x;
-  const int HW = m.H * m.W;
-  const float* gtn = m.gt_np ? m.gt_np + (long long)b * HW : nullptr;
+__global__ void __launch_bounds__(256) metrics_minmax_kernel(const MetricK m, MetricImg* ws) {
+  const int b = blockIdx.y, HW = m.H * m.W;
   const float* g = m.gt + (long long)b * HW;
   const float* p = m.pred + (long long)b * HW;
-  __shared__ float s_f[6][32];
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix;
-  __shared__ long long s_k;
-  __shared__ double sred[32 * 9];
-  __shared__ float s_mm[6];
-  // 1. per-image min / max (calculate_error.py:38-39 and the NYU / Make3D equivalents)
+  const float* gtn = m.gt_np ? m.gt_np + (long long)b * HW : nullptr;
   float v[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const float gv = g[i], pv = p[i];
     v[0] = fminf(v[0], gv); v[1] = fmaxf(v[1], gv);
     v[2] = fminf(v[2], pv); v[3] = fmaxf(v[3], pv);
@@ -358,7 +346,6 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
       v[4] = fminf(v[4], nv); v[5] = fmaxf(v[5], nv);
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -367,43 +354,105 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
       v[j] = (j & 1) ? fmaxf(v[j], t) : fminf(v[j], t);
     }
   }
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int j = 0; j < 6; j++) s_f[j][warp] = v[j];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int j = 0; j < 6; j++) {
-      float r = s_f[j][0];
-      for (int w = 1; w < nw; w++) r = (j & 1) ? fmaxf(r, s_f[j][w]) : fminf(r, s_f[j][w]);
-      s_mm[j] = r;
+    for (int j = 0; j < (VAR == 2 ? 6 : 4); j++) {
+      if (j & 1) atomicMax(&ws[b].mm[j], m_f2ord(v[j]));
+      else atomicMin(&ws[b].mm[j], m_f2ord(v[j]));
     }
   }
-  __syncthreads();
+}
+
+__device__ __forceinline__ MinMax metrics_load_mm(const MetricImg& w) {
   MinMax mm;
-  mm.gmin = s_mm[0]; mm.gmax = s_mm[1]; mm.pmin = s_mm[2]; mm.pmax = s_mm[3]; mm.nmin = s_mm[4]; mm.nmax = s_mm[5];
-  // 2. number of valid pixels
-  double cnt[1] = {0.0};
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    float vg, vp;
-    if (metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) cnt[0] += 1.0;
+  mm.gmin = m_ord2f(w.mm[0]); mm.gmax = m_ord2f(w.mm[1]); mm.pmin = m_ord2f(w.mm[2]); mm.pmax = m_ord2f(w.mm[3]);
+  mm.nmin = m_ord2f(w.mm[4]); mm.nmax = m_ord2f(w.mm[5]);
+  return mm;
+}
+
+// radix-select state after `passes` completed passes, recomputed by one thread per CTA from the global histograms
+// (<= 4 x 256 bins): value prefix, rank still to find, and the number of valid pixels (total of the first histogram)
+__device__ void metrics_select_state(const MetricImg& w, int passes, int which, unsigned int& prefix, long long& k,
+                                     long long& nvalid) {
+  long long n = 0;
+  for (int bin = 0; bin < 256; bin++) n += w.hist[0][0][bin];
+  nvalid = n;
+  prefix = 0;
+  k = n > 0 ? (n - 1) / 2 : 0;                  // lower median (torch.median), calculate_error.py:86 / :134 / :175
+  for (int ps = 0; ps < passes; ps++) {
+    const int shift = 24 - 8 * ps;
+    unsigned int bin = 0;
+    for (; bin < 255; bin++) {
+      const long long c = w.hist[ps][which][bin];
+      if (k < c) break;
+      k -= c;
+    }
+    prefix |= bin << shift;
   }
-  block_sum_d<1>(cnt, sred);
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(256) metrics_radix_kernel(const MetricK m, MetricImg* ws, const int pass) {
+  const int b = blockIdx.y, HW = m.H * m.W;
+  const float* g = m.gt + (long long)b * HW;
+  const float* p = m.pred + (long long)b * HW;
+  const float* gtn = m.gt_np ? m.gt_np + (long long)b * HW : nullptr;
+  __shared__ unsigned int hist[2][256];
+  __shared__ unsigned int s_prefix[2];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
+  if (threadIdx.x < 2) {
+    long long k, nv;
+    unsigned int pf;
+    metrics_select_state(ws[b], pass, threadIdx.x, pf, k, nv);
+    s_prefix[threadIdx.x] = pf;
+  }
+  __syncthreads();
+  const MinMax mm = metrics_load_mm(ws[b]);
+  const int shift = 24 - 8 * pass;
+  const unsigned int mask = pass ? (0xffffffffu << (shift + 8)) : 0u;
+  const unsigned int pg = s_prefix[0], pp = s_prefix[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float vg, vp;
+    if (!metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) continue;
+    const unsigned int bg = __float_as_uint(vg), bp = __float_as_uint(vp);
+    if ((bg & mask) == pg) atomicAdd(&hist[0][(bg >> shift) & 255u], 1u);
+    if ((bp & mask) == pp) atomicAdd(&hist[1][(bp >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const unsigned int c = (&hist[0][0])[i];
+    if (c) atomicAdd(&ws[b].hist[pass][0][0] + i, c);
+  }
+}
+
+template <int VAR>
+__global__ void __launch_bounds__(256) metrics_final_kernel(const MetricK m, MetricImg* ws) {
+  const int b = blockIdx.y, HW = m.H * m.W;
+  const float* g = m.gt + (long long)b * HW;
+  const float* p = m.pred + (long long)b * HW;
+  const float* gtn = m.gt_np ? m.gt_np + (long long)b * HW : nullptr;
+  __shared__ double sred[32 * 9];
+  __shared__ float s_med[2];
   __shared__ long long s_n;
-  if (threadIdx.x == 0) s_n = (long long)cnt[0];
+  __shared__ int s_last;
+  if (threadIdx.x < 2) {
+    long long k, nv;
+    unsigned int pf;
+    metrics_select_state(ws[b], 4, threadIdx.x, pf, k, nv);
+    s_med[threadIdx.x] = __uint_as_float(pf);
+    if (threadIdx.x == 0) s_n = nv;
+  }
   __syncthreads();
   const long long nvalid = s_n;
   if (nvalid == 0) {
-    if (threadIdx.x == 0 && m.counts) { for (int j = 0; j < 4; j++) m.counts[b * 4 + j] = 0; }
-    return;  // the reference would produce NaNs here; callers treat n_valid == 0 as "no measurement"
+    // the reference would produce NaNs here; callers treat n_valid == 0 as "no measurement"
+    if (blockIdx.x == 0 && threadIdx.x == 0 && m.counts) { for (int j = 0; j < 4; j++) m.counts[b * 4 + j] = 0; }
+    return;
   }
-  // 3. lower medians (torch.median), calculate_error.py:86 / :134 / :175
-  const long long kth = (nvalid - 1) / 2;
-  const float med_g = select_kth<VAR, false>(m, mm, gtn, g, p, kth, hist, &s_prefix, &s_k);
-  const float med_p = select_kth<VAR, true>(m, mm, gtn, g, p, kth, hist, &s_prefix, &s_k);
-  // 4. metrics
+  const MinMax mm = metrics_load_mm(ws[b]);
+  const float med_g = s_med[0], med_p = s_med[1];
   double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     float vg, vp;
     if (!metric_pixel<VAR>(m, mm, gtn, g, p, i, vg, vp)) continue;
     vp = __fdiv_rn(__fmul_rn(vp, med_g), med_p);
@@ -424,24 +473,46 @@ __global__ void __launch_bounds__(1024, 1) eigen_metrics_kernel(const MetricK m)
   }
   block_sum_d<9>(acc, sred);
   if (threadIdx.x == 0) {
-    const double n = (double)nvalid, invB = 1.0 / (double)m.B;
-    atomicAdd(m.out + 0, acc[0] / n * invB);
-    atomicAdd(m.out + 1, acc[1] / n * invB);
-    atomicAdd(m.out + 2, acc[2] / n * invB);
-    if (VAR != 2) {
-      atomicAdd(m.out + 3, (double)((float)acc[3] / (float)nvalid) * invB);
-      atomicAdd(m.out + 4, (double)((float)acc[4] / (float)nvalid) * invB);
-      atomicAdd(m.out + 5, (double)((float)acc[5] / (float)nvalid) * invB);
-      atomicAdd(m.out + 7, sqrt(acc[7] / n) * invB);
-    }
-    atomicAdd(m.out + 6, sqrt(acc[6] / n) * invB);
-    if (m.counts) {
-      m.counts[b * 4 + 0] = nvalid;
-      m.counts[b * 4 + 1] = (long long)acc[3];
-      m.counts[b * 4 + 2] = (long long)acc[4];
-      m.counts[b * 4 + 3] = (long long)acc[5];
-    }
+    for (int j = 0; j < 8; j++) atomicAdd(&ws[b].sums[j], acc[j]);
+    __threadfence();
+    s_last = (atomicAdd(&ws[b].done, 1u) == gridDim.x - 1) ? 1 : 0;
   }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  double t[8];
+  for (int j = 0; j < 8; j++) t[j] = atomicAdd(&ws[b].sums[j], 0.0);     // coherent read of the finished sums
+  const double n = (double)nvalid, invB = 1.0 / (double)m.B;
+  atomicAdd(m.out + 0, t[0] / n * invB);
+  atomicAdd(m.out + 1, t[1] / n * invB);
+  atomicAdd(m.out + 2, t[2] / n * invB);
+  if (VAR != 2) {
+    atomicAdd(m.out + 3, (double)((float)t[3] / (float)nvalid) * invB);
+    atomicAdd(m.out + 4, (double)((float)t[4] / (float)nvalid) * invB);
+    atomicAdd(m.out + 5, (double)((float)t[5] / (float)nvalid) * invB);
+    atomicAdd(m.out + 7, sqrt(t[7] / n) * invB);
+  }
+  atomicAdd(m.out + 6, sqrt(t[6] / n) * invB);
+  if (m.counts) {
+    m.counts[b * 4 + 0] = nvalid;
+    m.counts[b * 4 + 1] = (long long)t[3];
+    m.counts[b * 4 + 2] = (long long)t[4];
+    m.counts[b * 4 + 3] = (long long)t[5];
+  }
+}
+
+template <int VAR>
+static void metrics_launch(const MetricK& m, MetricImg* ws, cudaStream_t st) {
+  const int HW = m.H * m.W;
+  int chunks = (HW + 4095) / 4096;                       // >= 16 pixels per thread
+  const int cap = (device_sm_count() * 4 + m.B - 1) / m.B;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  const dim3 grid(chunks, m.B);
+  metrics_init_kernel<<<(m.B * (int)(sizeof(MetricImg) / 4) + 255) / 256, 256, 0, st>>>(ws, m.B);
+  metrics_minmax_kernel<VAR><<<grid, 256, 0, st>>>(m, ws);
+  for (int pass = 0; pass < 4; pass++) metrics_radix_kernel<VAR><<<grid, 256, 0, st>>>(m, ws, pass);
+  metrics_final_kernel<VAR><<<grid, 256, 0, st>>>(m, ws);
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
@@ -549,11 +620,17 @@ GDN_API int gdn_tanh_chain_add(const float* dout, const float* out, int64_t n, f
   return GDN_OK;
 }
 
+GDN_API size_t gdn_depth_metrics_workspace_bytes(int b) { return b > 0 ? (size_t)b * sizeof(MetricImg) : 0; }
+
 GDN_API int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, const float* pred, int b, int h, int w,
-                              int crop, double* out8, int64_t* counts, gdn_stream stream) {
+                              int crop, double* out8, int64_t* counts, void* workspace, size_t workspace_bytes,
+                              gdn_stream stream) {
   if (variant < 0 || variant > 2) return fail(GDN_INVALID_DESC, "gdn_depth_metrics: variant %d", variant);
   if ((!gt_np && variant != GDN_METRICS_NYU) || !gt || !pred || !out8 || b < 1)
     return fail(GDN_INVALID_DESC, "gdn_depth_metrics: bad arguments");
+  if (!workspace || workspace_bytes < gdn_depth_metrics_workspace_bytes(b) || (reinterpret_cast<uintptr_t>(workspace) & 7))
+    return fail(GDN_WORKSPACE_TOO_SMALL, "gdn_depth_metrics: needs %zu bytes of 8-byte aligned workspace",
+                gdn_depth_metrics_workspace_bytes(b));
   MetricK m{};
   m.gt_np = gt_np; m.gt = gt; m.pred = pred;
   m.B = b; m.H = h; m.W = w; m.crop = (variant == GDN_METRICS_MAKE3D) ? 0 : crop;
@@ -566,16 +643,17 @@ GDN_API int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, 
   m.cx1 = (int)(0.0359477 * w); m.cx2 = (int)(0.96405229 * w);
   m.out = out8;
   m.counts = reinterpret_cast<long long*>(counts);
-  if (variant == GDN_METRICS_KITTI) eigen_metrics_kernel<0><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
-  else if (variant == GDN_METRICS_NYU) eigen_metrics_kernel<1><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
-  else eigen_metrics_kernel<2><<<b, 1024, 0, (cudaStream_t)stream>>>(m);
-  GDN_LAUNCH_CHECK("eigen_metrics_kernel");
+  MetricImg* ws = reinterpret_cast<MetricImg*>(workspace);
+  if (variant == GDN_METRICS_KITTI) metrics_launch<0>(m, ws, (cudaStream_t)stream);
+  else if (variant == GDN_METRICS_NYU) metrics_launch<1>(m, ws, (cudaStream_t)stream);
+  else metrics_launch<2>(m, ws, (cudaStream_t)stream);
+  GDN_LAUNCH_CHECK("depth metrics kernels");
   return GDN_OK;
 }
 
 GDN_API int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
-                              double* out8, int64_t* counts, gdn_stream stream) {
-  return gdn_depth_metrics(GDN_METRICS_KITTI, gt_np, gt, pred, b, h, w, crop, out8, counts, stream);
+                              double* out8, int64_t* counts, void* workspace, size_t workspace_bytes, gdn_stream stream) {
+  return gdn_depth_metrics(GDN_METRICS_KITTI, gt_np, gt, pred, b, h, w, crop, out8, counts, workspace, workspace_bytes, stream);
 }
 
 GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -42,10 +42,11 @@ def eigen_metrics_device(gt_np, gt, pred, crop=True):
     out8 = torch.zeros(8, dtype=torch.float64, device=gt.device)
     counts = torch.zeros((B, 4), dtype=torch.int64, device=gt.device)
     L = _lib.lib()
+    ws = torch.empty(L.gdn_depth_metrics_workspace_bytes(B) // 8, dtype=torch.int64, device=gt.device)
     with torch.cuda.device(gt.device):
         rc = L.gdn_eigen_metrics(C.c_void_p(gt_np.data_ptr()), C.c_void_p(gt.data_ptr()), C.c_void_p(pred.data_ptr()),
                                  B, H, W, int(bool(crop)), C.c_void_p(out8.data_ptr()), C.c_void_p(counts.data_ptr()),
-                                 _lib.stream_ptr())
+                                 C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel() * 8), _lib.stream_ptr())
     _lib.check(rc, "eigen_metrics")
     return out8, counts
 
@@ -69,10 +70,12 @@ def _depth_metrics(variant, gt_np, gt, pred, crop):
     out8 = torch.zeros(8, dtype=torch.float64, device=gt.device)
     counts = torch.zeros((B, 4), dtype=torch.int64, device=gt.device)
     L = _lib.lib()
+    ws = torch.empty(L.gdn_depth_metrics_workspace_bytes(B) // 8, dtype=torch.int64, device=gt.device)
     with torch.cuda.device(gt.device):
         rc = L.gdn_depth_metrics(variant, C.c_void_p(gt_np.data_ptr() if gt_np is not None else None),
                                  C.c_void_p(gt.data_ptr()), C.c_void_p(pred.data_ptr()), B, H, W, int(bool(crop)),
-                                 C.c_void_p(out8.data_ptr()), C.c_void_p(counts.data_ptr()), _lib.stream_ptr())
+                                 C.c_void_p(out8.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                 C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel() * 8), _lib.stream_ptr())
     _lib.check(rc, "depth_metrics")
     return out8, counts
 

@@ -288,13 +288,19 @@ int gdn_sqdiff_grad(const float* a, const float* b, int64_t n, float coef, float
 /* dpre[i] += scale * dout[i] * (1 - out[i]^2): adds a gradient w.r.t. the network's tanh output to dL/d(pre-tanh) */
 int gdn_tanh_chain_add(const float* dout, const float* out, int64_t n, float scale, float* dpre, gdn_stream stream);
 
-/* calculate_error.compute_errors (calculate_error.py:10-103), one CTA per image, exact lower medians by radix
- * select.  out8 += [abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log] averaged over the b images (caller
- * zeroes); counts[b][4] = (n_valid, n(thr<1.25), n(thr<1.25^2), n(thr<1.25^3)) may be NULL. */
+/* calculate_error.compute_errors (calculate_error.py:10-103): per-image min-max normalisation, validity mask + crop,
+ * exact lower medians by radix select, median scaling, the 8 Eigen metrics.  Staged over many CTAs per image (min/max,
+ * four radix passes that histogram ground truth and prediction together, metric sums finished by the last CTA of each
+ * image); the per-pixel fp32 operation order is the reference's, so the delta-threshold COUNTS are bit-exact.
+ * out8 += [abs_diff, abs_rel, sq_rel, a1, a2, a3, rmse, rmse_log] averaged over the b images (caller zeroes);
+ * counts[b][4] = (n_valid, n(thr<1.25), n(thr<1.25^2), n(thr<1.25^3)) may be NULL.
+ * workspace: gdn_depth_metrics_workspace_bytes(b) bytes of caller-owned device memory (8-byte aligned; the library
+ * initialises it on the stream). */
+size_t gdn_depth_metrics_workspace_bytes(int b);
 int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
-                      double* out8, int64_t* counts, gdn_stream stream);
+                      double* out8, int64_t* counts, void* workspace, size_t workspace_bytes, gdn_stream stream);
 
-/* The same kernel with the constants of the other two evaluation protocols of calculate_error.py:
+/* The same kernels with the constants of the other two evaluation protocols of calculate_error.py:
  *   GDN_METRICS_KITTI  = compute_errors        (:10-103)  = gdn_eigen_metrics
  *   GDN_METRICS_NYU    = compute_errors_NYU    (:105-151): 10 m range, valid = 0 < gt < 10, border crop, clamp(1e-3, 10);
  *                        out8 = [abs_diff, abs_rel, log10, a1, a2, a3, rmse, rmse_log]; gt_np unused (may be NULL)
@@ -304,7 +310,7 @@ int gdn_eigen_metrics(const float* gt_np, const float* gt, const float* pred, in
 #define GDN_METRICS_NYU 1
 #define GDN_METRICS_MAKE3D 2
 int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, const float* pred, int b, int h, int w, int crop,
-                      double* out8, int64_t* counts, gdn_stream stream);
+                      double* out8, int64_t* counts, void* workspace, size_t workspace_bytes, gdn_stream stream);
 
 /* Fused Adam with coupled L2 decay over flat fp32 buffers (torch.optim.Adam semantics); step is 1-based;
  * the gradient is multiplied by grad_scale first. */
