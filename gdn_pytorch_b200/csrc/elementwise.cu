@@ -120,53 +120,66 @@ __global__ void im2col_kernel(const float* __restrict__ src, __nv_bfloat16* __re
 
 
 
-// shared-memory path (the one the networks use): the kh input rows an output row needs are staged ONCE per output row
-// in shared memory, pixel-interleaved ([row][x + pad][c], borders already reflected / zeroed), so that the kw*C columns
-// of one tap row are a contiguous run: column k of pixel x is s_rows[off(k) + x*C] with off(k) from a small table.
-// A warp writes one pixel's kpad columns with consecutive lanes on consecutive columns: conflict-free shared-memory
-// reads and fully coalesced 2-byte stores -- the kernel is bound by the HBM write of the column matrix.
+// shared-memory path (the one the networks use): a CTA iteration produces a BAND of up to kIm2colBand output rows; the
+// band's kh - 1 + band input rows are staged once in shared memory, pixel-interleaved ([row][x + pad][c], borders already
+// reflected / zeroed), so that the kw*C columns of one tap row are a contiguous run: column k of pixel x is
+// s_rows[off(k) + x*C] with off(k) from a small per-lane table.  A warp writes one pixel's kpad columns, each lane two
+// adjacent columns per store (128 contiguous bytes per warp instruction).  The first version staged kh rows per OUTPUT
+// row (9x re-staging with two integer divisions per element) and stored 2 bytes per lane: 1.7 TB/s on the column matrix
+// (profiles/r02e_ncu_elem.summary.txt).
+constexpr int kIm2colBand = 8;
+
 __global__ void __launch_bounds__(kEwThreads) im2col_smem_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                  int N, int C, int H, int W, int kh, int kw, int pad,
-                                                                 int reflect, int kpad) {
-  extern __shared__ float s_rows[];   // [kh][(W + 2*pad) * C]
+                                                                 int reflect, int kpad, int band_rows) {
+  extern __shared__ float s_rows[];   // [kh - 1 + band_rows][(W + 2*pad) * C]
   const int Wp = W + 2 * pad;
   const int rowstride = Wp * C;
   const int kreal = kh * kw * C, kwc = kw * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int off[8];                         // kpad <= 256: at most 8 columns per lane
+  int off[4][2];                      // kpad <= 256: at most 4 column pairs per lane
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const int k = j * 32 + lane;
-    off[j] = (k < kreal && k < kpad) ? (k / kwc) * rowstride + (k % kwc) : -1;
-  }
-  const int nj = kpad >> 5;
-  const int rows = N * H, plane = H * W;
-  const int fill = kh * rowstride;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int n = row / H, y = row - n * H;
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int k = j * 64 + 2 * lane + e;
+      off[j][e] = (k < kreal && k < kpad) ? (k / kwc) * rowstride + (k % kwc) : -1;
+    }
+  const int nj = kpad >> 6;
+  const int bands_img = (H + band_rows - 1) / band_rows;
+  const int bands = N * bands_img, plane = H * W;
+  for (int band = blockIdx.x; band < bands; band += gridDim.x) {
+    const int n = band / bands_img, y0 = (band - n * bands_img) * band_rows;
+    const int nr = min(band_rows, H - y0);
     const float* img = src + (size_t)n * C * plane;
     __syncthreads();
-    for (int i = threadIdx.x; i < fill; i += kEwThreads) {
-      const int r = i / rowstride, rem = i - r * rowstride;
-      const int c = rem / Wp, xp = rem - c * Wp;      // channel-major over the row: global reads run along x
-      int yy = y + r - pad, xx = xp - pad;
-      bool ok = true;
-      if (reflect) {
-        yy = reflect_idx(yy, H);
-        xx = reflect_idx(xx, W);
-      } else {
-        ok = (yy >= 0 && yy < H && xx >= 0 && xx < W);
+    for (int r = 0; r < nr + kh - 1; r++) {
+      int yy = y0 + r - pad;
+      const bool yok = reflect || (yy >= 0 && yy < H);
+      if (reflect) yy = reflect_idx(yy, H);
+      for (int c = 0; c < C; c++) {
+        const float* line = img + (size_t)c * plane + (size_t)(yok ? yy : 0) * W;
+        for (int xp = threadIdx.x; xp < Wp; xp += kEwThreads) {        // global reads run along x
+          int xx = xp - pad;
+          bool ok = yok;
+          if (reflect) xx = reflect_idx(xx, W);
+          else ok = ok && (xx >= 0 && xx < W);
+          s_rows[r * rowstride + xp * C + c] = ok ? __ldg(line + xx) : 0.f;
+        }
       }
-      s_rows[r * rowstride + xp * C + c] = ok ? __ldg(img + c * plane + yy * W + xx) : 0.f;
     }
     __syncthreads();
-    __nv_bfloat16* drow = dst + (size_t)row * W * kpad;
-    for (int x = warp; x < W; x += kEwThreads / 32) {
-      const float* base = s_rows + x * C;
-      __nv_bfloat16* o = drow + (size_t)x * kpad + lane;
+    for (int ry = 0; ry < nr; ry++) {
+      __nv_bfloat16* drow = dst + ((size_t)(n * H + y0 + ry) * W) * kpad;
+      const float* srow = s_rows + ry * rowstride;
+      for (int x = warp; x < W; x += kEwThreads / 32) {
+        const float* base = srow + x * C;
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(drow + (size_t)x * kpad) + lane;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        if (j < nj) o[j * 32] = __float2bfloat16(off[j] >= 0 ? base[off[j]] : 0.f);
+        for (int j = 0; j < 4; j++) {
+          if (j < nj)
+            o[j * 32] = __floats2bfloat162_rn(off[j][0] >= 0 ? base[off[j][0]] : 0.f, off[j][1] >= 0 ? base[off[j][1]] : 0.f);
+        }
       }
     }
   }
@@ -1111,17 +1124,21 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
     return fail(GDN_INVALID_DESC, "gdn_im2col: bad arguments (c=%d kpad=%d)", c, kpad);
   if (reflect && (pad >= h || pad >= w)) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_im2col: reflection pad %d >= extent", pad);
   {
-    const size_t smem = (size_t)kh * (w + 2 * pad) * c * sizeof(float);
-    if (kpad <= 256 && smem <= 96 * 1024 && (long long)h * w * c < (1ll << 31)) {
+    // band of output rows per CTA iteration: as many as fit 200 KB of shared memory next to the kh - 1 halo rows (<= 8)
+    const size_t row_bytes = (size_t)(w + 2 * pad) * c * sizeof(float);
+    int band = (int)((200 * 1024) / row_bytes) - (kh - 1);
+    if (band > kIm2colBand) band = kIm2colBand;
+    if (kpad <= 256 && kpad % 64 == 0 && band >= 1 && (long long)h * w * c < (1ll << 31)) {
+      const size_t smem = (size_t)(kh - 1 + band) * row_bytes;
       static bool configured[64] = {false};
       int dev = 0;
       cudaGetDevice(&dev);
       if (dev >= 0 && dev < 64 && !configured[dev]) {
-        GDN_CUDA_CHECK(cudaFuncSetAttribute(im2col_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        GDN_CUDA_CHECK(cudaFuncSetAttribute(im2col_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[dev] = true;
       }
-      im2col_smem_kernel<<<ew_row_grid((long long)n * h), kEwThreads, smem, (cudaStream_t)stream>>>(
-          src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad);
+      im2col_smem_kernel<<<ew_row_grid((long long)n * ((h + band - 1) / band)), kEwThreads, smem, (cudaStream_t)stream>>>(
+          src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad, band);
       GDN_LAUNCH_CHECK("im2col_smem_kernel");
       return GDN_OK;
     }

@@ -1159,7 +1159,12 @@ class Engine:
         Runs at engine construction, before any real data is in the buffers; GDN_AUTOTUNE=0 keeps the heuristics."""
         self.algo_choice = {}
         cache = {}
-        if os.environ.get("GDN_SPLITK", "1") != "0":
+        # split-K is OPT-IN (GDN_SPLITK=1).  Measured on the B200 with graph-captured timing (profiles/r02f_sweep_conv.log):
+        # the 512-channel 8x26 layers go from 47.0 to 43.1 us -- they are bound by the weight tiles every CTA pulls from L2
+        # (2.3 MB per CTA at 128-byte granularity), not by the number of pixel tiles, so splitting the reduction moves
+        # little; and a time-picked split changes the fp32 summation order, which would make two engines (two ranks, graph
+        # vs eager, demo replay vs eager) differ in the last bits.  Without it every variant is bit-identical.
+        if os.environ.get("GDN_SPLITK", "0") == "1":
             self._attach_splitk_workspace()
         for what, d in self._conv_descs:
             key = (d.src0.n, d.src0.h, d.src0.w, d.src0.c, d.src0.pad, d.src1.c if d.src1.ptr else 0, d.kh, d.kw, d.stride,
