@@ -1,4 +1,5 @@
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -31,6 +32,18 @@ int device_sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  // OPT-IN (GDN_PDL=1).  Measured on the B200, same box, back to back (profiles/r02k_bench_*.json): inference (one
+  // stream) 1219.8 -> 1231.7 img/s, but the training step 536 -> 488 img/s: an early-launched convolution CTA holds its
+  // 225 KB of shared memory while it waits, which keeps the side-stream weight-gradient kernels from co-running with the
+  // BatchNorm-backward kernels of the main chain -- the overlap the step's stream schedule is built on.
+  static const bool on = [] {
+    const char* e = getenv("GDN_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -25,6 +25,47 @@ int device_sm_count();
     if (_e != cudaSuccess) return ::gdn::fail(GDN_CUDA_ERROR, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
 
+// Programmatic dependent launch (PDL).  Every kernel of the step chain starts with pdl_trigger() -- "the next kernel of
+// this stream may be scheduled now": its launch latency and its prologue (barrier init, tensor-memory allocation,
+// tensor-map prefetch) overlap THIS kernel -- and executes pdl_wait() before it touches global memory: the wait returns
+// when the preceding kernel of the stream has completed and flushed.  Because every kernel launched through
+// launch_pdl() waits before it finishes, completion stays transitive along the stream (kernel N+2 never overtakes N).
+// Without the launch attribute (the default: GDN_PDL=1 opts in, see pdl_enabled(); or a launch that does not go through
+// launch_pdl) both are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+// Launch `kern` (which MUST execute pdl_wait()) on `st`, optionally as clusters of `cluster_x` CTAs.
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned na = 0;
+  if (cluster_x > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster_x;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..rank-1.
 int encode_tmap_bf16(CUtensorMap* out, void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box);

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvK p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();   // the next kernel of the stream may set up while this one runs (it waits for our completion itself)
   // (the dynamic shared memory starts at the same offset in both CTAs of a pair, so the aligned layout is symmetric)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr uint32_t B_BYTES = BN * 128 / CG;   // a pair splits the weight rows between its CTAs
@@ -176,6 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmA1);
   }
   if (warp == kWarpB && lane == 0) tma_prefetch_desc(&tmB);
+  pdl_wait();      // everything above overlapped the preceding kernel; its results are visible from here on
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised too
   tc_fence_after();
@@ -607,6 +609,8 @@ struct CombK {
 
 __global__ void __launch_bounds__(256) conv_splitk_combine_kernel(const CombK k) {
   extern __shared__ float s_red[];   // [2][C]
+  pdl_trigger();
+  pdl_wait();
   const int cg = k.C >> 3;
   const int c8 = (threadIdx.x & (cg - 1)) * 8;
   const bool fstats = k.stat_sum && !k.bs_raw, bstats = k.bs_raw != nullptr;
@@ -725,23 +729,7 @@ static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMa
   }
   const int slots = device_sm_count() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int units = k.total_tiles < slots ? k.total_tiles : slots;
-  if (CG == 1) {
-    conv_igemm_kernel<BN, CG><<<units, kThreads, smem, st>>>(a0, a1, b, k);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(units * CG);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CG;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    GDN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, CG>, a0, a1, b, k));
-  }
+  GDN_CUDA_CHECK(launch_pdl(conv_igemm_kernel<BN, CG>, dim3(units * CG), dim3(kThreads), smem, st, CG, a0, a1, b, k));
   GDN_LAUNCH_CHECK("conv_igemm_kernel");
   return GDN_OK;
 }
@@ -961,7 +949,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)device_sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  conv_splitk_combine_kernel<<<(int)blocks, 256, 2 * c.C * sizeof(float), st>>>(c);
+  GDN_CUDA_CHECK(launch_pdl(conv_splitk_combine_kernel, dim3((int)blocks), dim3(256), 2 * c.C * sizeof(float), st, 1, c));
   GDN_LAUNCH_CHECK("conv_splitk_combine_kernel");
   return GDN_OK;
 }

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ WgK p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
   uint8_t* sY = smem + (size_t)p.nstage * p.x_bytes;
@@ -98,6 +99,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
     tma_prefetch_desc(&tmX1);
   }
   if (warp == kWgWarpY && lane == 0) tma_prefetch_desc(&tmY);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -503,9 +505,10 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
   }
   const size_t smem = (size_t)k.nstage * (k.x_bytes + k.y_bytes) + 1024;
   const int grid = k.total_work < sms ? k.total_work : sms;
-  if (WN == 256) conv_wgrad_kernel<256><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
-  else if (WN == 128) conv_wgrad_kernel<128><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
-  else conv_wgrad_kernel<64><<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX0, tmX1, tmY, k);
+  const cudaStream_t cs = (cudaStream_t)stream;
+  if (WN == 256) GDN_CUDA_CHECK(launch_pdl(conv_wgrad_kernel<256>, dim3(grid), dim3(kWgThreads), smem, cs, 1, tmX0, tmX1, tmY, k));
+  else if (WN == 128) GDN_CUDA_CHECK(launch_pdl(conv_wgrad_kernel<128>, dim3(grid), dim3(kWgThreads), smem, cs, 1, tmX0, tmX1, tmY, k));
+  else GDN_CUDA_CHECK(launch_pdl(conv_wgrad_kernel<64>, dim3(grid), dim3(kWgThreads), smem, cs, 1, tmX0, tmX1, tmY, k));
   GDN_LAUNCH_CHECK("conv_wgrad_kernel");
   return GDN_OK;
 }

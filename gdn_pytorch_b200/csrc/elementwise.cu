@@ -85,6 +85,8 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // src: fp32 planar [N][C][H][W] (C <= 4).  dst: bf16 [N*H*W][kpad], k = (r*kw + s)*C + c, zero beyond kh*kw*C.
 __global__ void im2col_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C, int H,
                               int W, int kh, int kw, int pad, int reflect, int kpad) {
+  pdl_trigger();
+  pdl_wait();
   const int kreal = kh * kw * C;
   const int groups = kpad / 8;
   const long long total = (long long)N * H * W * groups;
@@ -132,6 +134,8 @@ constexpr int kIm2colBand = 8;
 __global__ void __launch_bounds__(kEwThreads) im2col_smem_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                  int N, int C, int H, int W, int kh, int kw, int pad,
                                                                  int reflect, int kpad, int band_rows) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_rows[];   // [kh - 1 + band_rows][(W + 2*pad) * C]
   const int Wp = W + 2 * pad;
   const int rowstride = Wp * C;
@@ -191,6 +195,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ rstd_out, float4* __restrict__ coef4, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double m = sum[c] / count;
@@ -253,6 +259,8 @@ __device__ __forceinline__ void act_value8(const ActFwd& a, long long pix, int c
 
 // source coordinate + weight of F.interpolate(scale_factor=2, mode='bilinear')
 __global__ void act_forward_kernel(const ActFwd a) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = a.C / 8;
   const long long n_f32 = a.out_f32 ? (long long)a.N * a.H * a.W * cg : 0;
   const int OH = (a.up || a.dilate) ? 2 * a.H : a.H, OW = (a.up || a.dilate) ? 2 * a.W : a.W;
@@ -349,6 +357,8 @@ __device__ __forceinline__ void act_finish8(const ActFwd& a, float* v, const flo
 // 2 with one) so that ~64 KB of loads are outstanding per SM.
 template <bool RESID, int U>
 __global__ void __launch_bounds__(kEwThreads, 3) act_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int cgm = (1 << lg_cg) - 1;
   const int items = a.W << lg_cg;
   const int c8 = (threadIdx.x & cgm) * 8;
@@ -427,6 +437,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) act_rows_kernel(const ActFwd a,
 // output-driven x2 bilinear upsampling (align_corners=False) with an optional reflection border: one padded output
 // row per CTA iteration; the row's two source rows and the vertical weight are computed once per row.
 __global__ void __launch_bounds__(kEwThreads, 3) act_up_rows_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int cgm = (1 << lg_cg) - 1;
   const int OH = 2 * a.H, OW = 2 * a.W;
   const int P = a.P, Hp = OH + 2 * P, Wp = OW + 2 * P;
@@ -508,6 +520,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) act_up_rows_kernel(const ActFwd
 // act_up_rows_kernel re-reads four sources and redoes the coordinate arithmetic per OUTPUT (1.4 TB/s at the bench
 // shapes, profiles/r02e_ncu_elem.summary.txt); it stays for the fused BatchNorm / residual / fp32-source forms.
 __global__ void __launch_bounds__(kEwThreads, 3) up2x_blocks_kernel(const ActFwd a, const int lg_cg, const int rows) {
+  pdl_trigger();
+  pdl_wait();
   const int cgm = (1 << lg_cg) - 1;
   const int OH = 2 * a.H, OW = 2 * a.W;
   const int P = a.P, Hp = OH + 2 * P, Wp = OW + 2 * P;
@@ -608,6 +622,8 @@ __device__ __forceinline__ void bn_grad8(const BnBwd& b, size_t off, float* d) {
 // reads contiguous NHWC bytes.  Partials go block-level through shared-memory atomics, then one fp64 atomic per
 // channel per block.
 __global__ void bn_bwd_reduce_kernel(const BnBwd b) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [2][C]
   const int cgs = b.C / 8;
   const int lanes = blockDim.x / cgs;
@@ -655,6 +671,8 @@ __global__ void bn_bwd_reduce_kernel(const BnBwd b) {
 }
 
 __global__ void bn_bwd_apply_kernel(const BnBwd b) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = b.C / 8;
   const int OH = b.dilate ? 2 * b.H : b.H, OW = b.dilate ? 2 * b.W : b.W;
   const long long N = b.npix / ((long long)b.H * b.W);
@@ -718,6 +736,8 @@ __device__ __forceinline__ void bn_load8(const BnBwd& b, size_t off, float* x, f
 
 // per-channel sums of g and g*(x - mean) (scaled by rstd at the end); items = npix * cg, block-contiguous chunks
 __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const BnBwd b, const int lg_cg, const int chunk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [2][C]
   const int cgm = (1 << lg_cg) - 1;
   const int c8 = (threadIdx.x & cgm) * 8;
@@ -768,6 +788,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const
 // 32 B per item leave the kernel latency-bound at 2: 3.2 TB/s measured, profiles/r02c_profile_ops.log).
 template <int U>
 __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const BnBwd b, const int lg_cg, const int chunk) {
+  pdl_trigger();
+  pdl_wait();
   const int cgm = (1 << lg_cg) - 1;
   const int c8 = (threadIdx.x & cgm) * 8;
   const double inv_n = 1.0 / (double)b.npix;
@@ -814,6 +836,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
 
 // -------------------------------------------------------------------------------------------- fold grad
 __global__ void fold_grad_kernel(const FoldK f) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = f.C / 4;
   const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
   const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
@@ -880,6 +904,8 @@ __global__ void fold_grad_kernel(const FoldK f) {
 // item was ALU-bound at ~1 TB/s on the x2-bilinear adjoints; same-box A/B in profiles/r02a_*).  Dynamic shared memory:
 // W * 64 bytes.
 __global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char s_fold[];
   int* s_pc = reinterpret_cast<int*>(s_fold);                                  // [W][12]
   float* s_qw = reinterpret_cast<float*>(s_fold + (size_t)f.W * kFoldColInts * sizeof(int));   // [W][4]
@@ -913,6 +939,8 @@ struct FrozenBwd {
 };
 
 __global__ void __launch_bounds__(kEwThreads) frozen_bwd_kernel(const FrozenBwd b) {
+  pdl_trigger();
+  pdl_wait();
   const int cg = b.C / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < b.items; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cg) * 8;
@@ -943,6 +971,8 @@ __global__ void __launch_bounds__(kEwThreads) frozen_bwd_kernel(const FrozenBwd 
 
 // adjoint of reflection padding for thin (C not a multiple of 4) tensors: the input gradient of a first layer
 __global__ void fold_thin_kernel(const FoldK f) {
+  pdl_trigger();
+  pdl_wait();
   const int Hq = f.H + 2 * f.P, Wq = f.W + 2 * f.P;
   const long long total = (long long)f.N * f.H * f.W * f.C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -967,6 +997,8 @@ __global__ void fold_thin_kernel(const FoldK f) {
 // For im2col'd layers (col_c > 0): packed[0][a][k], k = (r*kw + s)*col_c + c  <->  w[a*sa + c*sb + r*sr + s*ss].
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
                                     __nv_bfloat16* __restrict__ out, const PackK k) {
+  pdl_trigger();
+  pdl_wait();
   const int T = k.col_c ? 1 : k.kh * k.kw;
   const long long total = (long long)T * k.Apad * k.Bpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -995,6 +1027,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
 
 // grad[w index] (+)= packed_dw[t][b][a]   (wgrad layout: [tap][ci = b][co = a], co padded to Apad)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int T = k.col_c ? 1 : k.kh * k.kw;
   const long long total = (long long)T * k.B * k.A;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1039,6 +1073,8 @@ struct PackJob {
 
 __global__ void __launch_bounds__(256) pack_tile2_kernel(const float* __restrict__ w, const float* __restrict__ scale_a,
                                                         __nv_bfloat16* __restrict__ out, const PackK k, const int tb) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_tile[];
   const int a0 = blockIdx.y * kPackTA, b0 = blockIdx.x * tb;
   pack_v2_phase1(w, k, a0, b0, tb, s_tile, threadIdx.x, blockDim.x);
@@ -1047,6 +1083,8 @@ __global__ void __launch_bounds__(256) pack_tile2_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restrict__ jobs, const int njobs) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_tile[];
   __shared__ PackJob job;
   if (threadIdx.x == 0) {
@@ -1068,6 +1106,8 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restri
 // grad[a*sa + b*sb + tap] (+)= dw[t][b][a]
 __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k,
                                                          int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_tile[];
   const int T = k.kh * k.kw;
   const int a0 = blockIdx.y * kPackTile, b0 = blockIdx.x * kPackTile;
@@ -1106,6 +1146,8 @@ static bool pack_tileable(const PackK& k) {
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ rmean, const float* __restrict__ rvar, float eps,
                                float* __restrict__ scale, float* __restrict__ bias, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float s = gamma[c] / sqrtf(rvar[c] + eps);
@@ -1137,15 +1179,13 @@ GDN_API int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, 
         GDN_CUDA_CHECK(cudaFuncSetAttribute(im2col_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[dev] = true;
       }
-      im2col_smem_kernel<<<ew_row_grid((long long)n * ((h + band - 1) / band)), kEwThreads, smem, (cudaStream_t)stream>>>(
-          src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad, band);
+      GDN_CUDA_CHECK(launch_pdl(im2col_smem_kernel, dim3(ew_row_grid((long long)n * ((h + band - 1) / band))), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad, band));
       GDN_LAUNCH_CHECK("im2col_smem_kernel");
       return GDN_OK;
     }
   }
   const long long work = (long long)n * h * w * (kpad / 8);
-  im2col_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad,
-                                                                      reflect, kpad);
+  GDN_CUDA_CHECK(launch_pdl(im2col_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, src, (__nv_bfloat16*)dst, n, c, h, w, kh, kw, pad, reflect, kpad));
   GDN_LAUNCH_CHECK("im2col_kernel");
   return GDN_OK;
 }
@@ -1155,16 +1195,14 @@ GDN_API int gdn_bn_finalize(const double* sum, const double* sqsum, double count
                             float* shift, float* mean, float* rstd, float* coef4, int c, gdn_stream stream) {
   if (!sum || !sqsum || !gamma || !beta || !scale || !shift || !mean || !rstd || c < 1)
     return fail(GDN_INVALID_DESC, "gdn_bn_finalize: null pointer");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sqsum, count, gamma, beta, eps, momentum,
-                                                                     running_mean, running_var, scale, shift, mean, rstd,
-                                                                     reinterpret_cast<float4*>(coef4), c);
+  GDN_CUDA_CHECK(launch_pdl(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, sum, sqsum, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, rstd, reinterpret_cast<float4*>(coef4), c));
   GDN_LAUNCH_CHECK("bn_finalize_kernel");
   return GDN_OK;
 }
 
 GDN_API int gdn_bn_fold(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
                         float* scale, float* bias, int c, gdn_stream stream) {
-  bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, rmean, rvar, eps, scale, bias, c);
+  GDN_CUDA_CHECK(launch_pdl(bn_fold_kernel, dim3((c + 127) / 128), dim3(128), 0, (cudaStream_t)stream, 1, gamma, beta, rmean, rvar, eps, scale, bias, c));
   GDN_LAUNCH_CHECK("bn_fold_kernel");
   return GDN_OK;
 }
@@ -1199,8 +1237,8 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
     if (a.up) lo.out_bf16 = nullptr;
     if (lo.out_f32 || lo.out_bf16) {
       const int rows = a.N * a.H;
-      if (lo.resid) act_rows_kernel<true, 2><<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
-      else act_rows_kernel<false, 4><<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(lo, lg, rows);
+      if (lo.resid) GDN_CUDA_CHECK(launch_pdl(act_rows_kernel<true, 2>, dim3(ew_row_grid(rows)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, lo, lg, rows));
+      else GDN_CUDA_CHECK(launch_pdl(act_rows_kernel<false, 4>, dim3(ew_row_grid(rows)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, lo, lg, rows));
       GDN_LAUNCH_CHECK("act_rows_kernel");
     }
     if (a.up && a.out_bf16) {
@@ -1208,17 +1246,17 @@ GDN_API int gdn_act_forward(const gdn_act_fwd_desc* d, gdn_stream stream) {
                         a.P < 2 * a.H && a.P < 2 * a.W;
       if (pure) {
         const int rows = a.N * (a.H + 1);
-        up2x_blocks_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
+        GDN_CUDA_CHECK(launch_pdl(up2x_blocks_kernel, dim3(ew_row_grid(rows)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, a, lg, rows));
         GDN_LAUNCH_CHECK("up2x_blocks_kernel");
       } else {
         const int rows = a.N * (OH + 2 * a.P);
-        act_up_rows_kernel<<<ew_row_grid(rows), kEwThreads, 0, (cudaStream_t)stream>>>(a, lg, rows);
+        GDN_CUDA_CHECK(launch_pdl(act_up_rows_kernel, dim3(ew_row_grid(rows)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, a, lg, rows));
         GDN_LAUNCH_CHECK("act_up_rows_kernel");
       }
     }
     return GDN_OK;
   }
-  act_forward_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  GDN_CUDA_CHECK(launch_pdl(act_forward_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, a));
   GDN_LAUNCH_CHECK("act_forward_kernel");
   return GDN_OK;
 }
@@ -1256,7 +1294,7 @@ GDN_API int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream) {
       chunk = (chunk + 2 * kEwThreads - 1) / (2 * kEwThreads) * (2 * kEwThreads);
       if (chunk < (1ll << 30)) {
         const int grid = (int)((total + chunk - 1) / chunk);
-        bn_bwd_reduce_fast_kernel<<<grid, kEwThreads, 2 * b.C * sizeof(float), (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        GDN_CUDA_CHECK(launch_pdl(bn_bwd_reduce_fast_kernel, dim3(grid), dim3(kEwThreads), 2 * b.C * sizeof(float), (cudaStream_t)stream, 1, b, lg, (int)chunk));
         GDN_LAUNCH_CHECK("bn_bwd_reduce_fast_kernel");
         return GDN_OK;
       }
@@ -1266,7 +1304,7 @@ GDN_API int gdn_bn_bwd_reduce(const gdn_bn_bwd_desc* d, gdn_stream stream) {
   long long blocks = (b.npix + lanes - 1) / lanes;
   const long long cap = (long long)device_sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, 2 * b.C * sizeof(float), (cudaStream_t)stream>>>(b);
+  GDN_CUDA_CHECK(launch_pdl(bn_bwd_reduce_kernel, dim3((int)blocks), dim3(kEwThreads), 2 * b.C * sizeof(float), (cudaStream_t)stream, 1, b));
   GDN_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return GDN_OK;
 }
@@ -1285,15 +1323,15 @@ GDN_API int gdn_act_backward(const gdn_bn_bwd_desc* d, gdn_stream stream) {
       chunk = (chunk + 4 * kEwThreads - 1) / (4 * kEwThreads) * (4 * kEwThreads);
       if (chunk < (1ll << 30)) {
         const int grid = (int)((total + chunk - 1) / chunk);
-        if (b.dact_bf16) bn_bwd_apply_fast_kernel<4><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
-        else bn_bwd_apply_fast_kernel<2><<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(b, lg, (int)chunk);
+        if (b.dact_bf16) GDN_CUDA_CHECK(launch_pdl(bn_bwd_apply_fast_kernel<4>, dim3(grid), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, b, lg, (int)chunk));
+        else GDN_CUDA_CHECK(launch_pdl(bn_bwd_apply_fast_kernel<2>, dim3(grid), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, b, lg, (int)chunk));
         GDN_LAUNCH_CHECK("bn_bwd_apply_fast_kernel");
         return GDN_OK;
       }
     }
   }
   const long long work = b.npix * (b.dilate ? 4 : 1) * (b.C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+  GDN_CUDA_CHECK(launch_pdl(bn_bwd_apply_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, b));
   GDN_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return GDN_OK;
 }
@@ -1313,7 +1351,7 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
   f.dpad_bf16 = d->dpad_is_bf16;
   if (thin && f.dpad_bf16) return fail(GDN_UNSUPPORTED_SHAPE, "gdn_fold_grad: bf16 input needs channel counts that are multiples of 4");
   if (thin) {
-    fold_thin_kernel<<<ew_grid((long long)f.N * f.H * f.W * f.C), kEwThreads, 0, (cudaStream_t)stream>>>(f);
+    GDN_CUDA_CHECK(launch_pdl(fold_thin_kernel, dim3(ew_grid((long long)f.N * f.H * f.W * f.C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, f));
     GDN_LAUNCH_CHECK("fold_thin_kernel");
     return GDN_OK;
   }
@@ -1323,14 +1361,14 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
       const int rows = f.N * f.H;
       const size_t smem = (size_t)f.W * (kFoldColInts * sizeof(int) + 4 * sizeof(float));
       if (smem <= 40 * 1024) {
-        fold_rows2_kernel<<<ew_row_grid(rows), kEwThreads, smem, (cudaStream_t)stream>>>(f, lg, rows);
+        GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
         GDN_LAUNCH_CHECK("fold_rows2_kernel");
         return GDN_OK;
       }
     }
   }
   const long long work = (long long)f.N * f.H * f.W * (f.C / 4);
-  fold_grad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(f);
+  GDN_CUDA_CHECK(launch_pdl(fold_grad_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, f));
   GDN_LAUNCH_CHECK("fold_grad_kernel");
   return GDN_OK;
 }
@@ -1345,7 +1383,7 @@ GDN_API int gdn_act_backward_frozen(const gdn_frozen_bwd_desc* d, gdn_stream str
   b.items = (long long)d->n * d->h * d->w * (d->c / 8);
   b.dy = (__nv_bfloat16*)d->dy;
   if (b.items == 0) return GDN_OK;
-  frozen_bwd_kernel<<<ew_grid(b.items), kEwThreads, 0, (cudaStream_t)stream>>>(b);
+  GDN_CUDA_CHECK(launch_pdl(frozen_bwd_kernel, dim3(ew_grid(b.items)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, b));
   GDN_LAUNCH_CHECK("frozen_bwd_kernel");
   return GDN_OK;
 }
@@ -1371,12 +1409,12 @@ GDN_API int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float
     }
     const int tb = pack_tb_for_taps(T);
     dim3 grid2((k.Bpad + tb - 1) / tb, (k.Apad + kPackTA - 1) / kPackTA);
-    pack_tile2_kernel<<<grid2, 256, pack_smem_bytes(T), (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k, tb);
+    GDN_CUDA_CHECK(launch_pdl(pack_tile2_kernel, dim3(grid2), dim3(256), pack_smem_bytes(T), (cudaStream_t)stream, 1, w, scale_a, (__nv_bfloat16*)out, k, tb));
     GDN_LAUNCH_CHECK("pack_tile2_kernel");
     return GDN_OK;
   }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.Apad * k.Bpad;
-  pack_weights_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(w, scale_a, (__nv_bfloat16*)out, k);
+  GDN_CUDA_CHECK(launch_pdl(pack_weights_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, w, scale_a, (__nv_bfloat16*)out, k));
   GDN_LAUNCH_CHECK("pack_weights_kernel");
   return GDN_OK;
 }
@@ -1419,7 +1457,7 @@ GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ct
     GDN_CUDA_CHECK(cudaFuncSetAttribute(pack_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured[dev] = true;
   }
-  pack_table_kernel<<<total_ctas, 256, smem, (cudaStream_t)stream>>>((const PackJob*)jobs_dev, njobs);
+  GDN_CUDA_CHECK(launch_pdl(pack_table_kernel, dim3(total_ctas), dim3(256), smem, (cudaStream_t)stream, 1, (const PackJob*)jobs_dev, njobs));
   GDN_LAUNCH_CHECK("pack_table_kernel");
   return GDN_OK;
 }
@@ -1439,12 +1477,12 @@ GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* gra
       configured[dev] = true;
     }
     dim3 grid((k.B + kPackTile - 1) / kPackTile, (k.A + kPackTile - 1) / kPackTile);
-    unpack_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dw, grad, k, accumulate);
+    GDN_CUDA_CHECK(launch_pdl(unpack_tile_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 1, dw, grad, k, accumulate));
     GDN_LAUNCH_CHECK("unpack_tile_kernel");
     return GDN_OK;
   }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.A * k.B;
-  unpack_wgrad_kernel<<<ew_grid(work), kEwThreads, 0, (cudaStream_t)stream>>>(dw, grad, k, accumulate);
+  GDN_CUDA_CHECK(launch_pdl(unpack_wgrad_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, dw, grad, k, accumulate));
   GDN_LAUNCH_CHECK("unpack_wgrad_kernel");
   return GDN_OK;
 }

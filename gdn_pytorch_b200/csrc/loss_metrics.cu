@@ -42,6 +42,8 @@ __device__ __forceinline__ void block_sum_d(double (&v)[NV], double* smem /* [32
 // --------------------------------------------------------------------------------------- max |a - b|
 __global__ void absdiff_max_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                    unsigned int* __restrict__ out_bits) {
+  pdl_trigger();
+  pdl_wait();
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     m = fmaxf(m, fabsf(a[i] - b[i]));
@@ -95,6 +97,8 @@ __device__ __forceinline__ void sobel_at(const float* __restrict__ img, int H, i
 }
 
 __global__ void loss_kernel(const LossK k) {
+  pdl_trigger();
+  pdl_wait();
   const long long HW = (long long)k.H * k.W;
   const long long total = (long long)k.N * HW;
   const float c = 0.2f * (*k.maxabs);
@@ -203,6 +207,8 @@ __global__ void loss_kernel(const LossK k) {
 // ------------------------------------------------------------------------------- sum of squared diffs
 __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
                                   double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   double acc[1] = {0.0};
   float part = 0.f;
   int cnt = 0;
@@ -227,6 +233,8 @@ __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __re
 // g[i] = coef * (a[i] - b[i]): gradient of coef/2 * sum (a - b)^2 w.r.t. a (one feature-MSE term of the latent loss)
 __global__ void sqdiff_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float coef,
                                    float* __restrict__ g) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 x = reinterpret_cast<const float4*>(a)[i];
     const float4 y = reinterpret_cast<const float4*>(b)[i];
@@ -237,6 +245,8 @@ __global__ void sqdiff_grad_kernel(const float* __restrict__ a, const float* __r
 // dpre[i] += scale * dout[i] * (1 - out[i]^2): chains a gradient w.r.t. the tanh output onto dL/d(pre-tanh)
 __global__ void tanh_chain_add_kernel(const float* __restrict__ dout, const float* __restrict__ out, long long n, float scale,
                                       float* __restrict__ dpre) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float o = out[i];
     dpre[i] += scale * dout[i] * (1.f - o * o);
@@ -322,6 +332,8 @@ __device__ __forceinline__ float m_ord2f(unsigned int u) {
 }
 
 __global__ void metrics_init_kernel(MetricImg* ws, int B) {
+  pdl_trigger();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * (int)(sizeof(MetricImg) / 4); i += gridDim.x * blockDim.x) {
     const int img = i / (int)(sizeof(MetricImg) / 4), w = i - img * (int)(sizeof(MetricImg) / 4);
     unsigned int v = 0u;
@@ -332,6 +344,8 @@ __global__ void metrics_init_kernel(MetricImg* ws, int B) {
 
 template <int VAR>
 __global__ void __launch_bounds__(256) metrics_minmax_kernel(const MetricK m, MetricImg* ws) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, HW = m.H * m.W;
   const float* g = m.gt + (long long)b * HW;
   const float* p = m.pred + (long long)b * HW;
@@ -393,6 +407,8 @@ __device__ void metrics_select_state(const MetricImg& w, int passes, int which, 
 
 template <int VAR>
 __global__ void __launch_bounds__(256) metrics_radix_kernel(const MetricK m, MetricImg* ws, const int pass) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, HW = m.H * m.W;
   const float* g = m.gt + (long long)b * HW;
   const float* p = m.pred + (long long)b * HW;
@@ -427,6 +443,8 @@ __global__ void __launch_bounds__(256) metrics_radix_kernel(const MetricK m, Met
 
 template <int VAR>
 __global__ void __launch_bounds__(256) metrics_final_kernel(const MetricK m, MetricImg* ws) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y, HW = m.H * m.W;
   const float* g = m.gt + (long long)b * HW;
   const float* p = m.pred + (long long)b * HW;
@@ -502,17 +520,18 @@ __global__ void __launch_bounds__(256) metrics_final_kernel(const MetricK m, Met
 }
 
 template <int VAR>
-static void metrics_launch(const MetricK& m, MetricImg* ws, cudaStream_t st) {
+static int metrics_launch(const MetricK& m, MetricImg* ws, cudaStream_t st) {
   const int HW = m.H * m.W;
   int chunks = (HW + 4095) / 4096;                       // >= 16 pixels per thread
   const int cap = (device_sm_count() * 4 + m.B - 1) / m.B;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   const dim3 grid(chunks, m.B);
-  metrics_init_kernel<<<(m.B * (int)(sizeof(MetricImg) / 4) + 255) / 256, 256, 0, st>>>(ws, m.B);
-  metrics_minmax_kernel<VAR><<<grid, 256, 0, st>>>(m, ws);
-  for (int pass = 0; pass < 4; pass++) metrics_radix_kernel<VAR><<<grid, 256, 0, st>>>(m, ws, pass);
-  metrics_final_kernel<VAR><<<grid, 256, 0, st>>>(m, ws);
+  GDN_CUDA_CHECK(launch_pdl(metrics_init_kernel, dim3((m.B * (int)(sizeof(MetricImg) / 4) + 255) / 256), dim3(256), 0, st, 1, ws, m.B));
+  GDN_CUDA_CHECK(launch_pdl(metrics_minmax_kernel<VAR>, dim3(grid), dim3(256), 0, st, 1, m, ws));
+  for (int pass = 0; pass < 4; pass++) GDN_CUDA_CHECK(launch_pdl(metrics_radix_kernel<VAR>, dim3(grid), dim3(256), 0, st, 1, m, ws, pass));
+  GDN_CUDA_CHECK(launch_pdl(metrics_final_kernel<VAR>, dim3(grid), dim3(256), 0, st, 1, m, ws));
+  return GDN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ Adam
@@ -522,6 +541,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
                             float eps, float wd, float grad_scale, const float* __restrict__ dyn, double b1d,
                             double b2d) {
+  pdl_trigger();
+  pdl_wait();
   if (dyn) {  // learning rate and step count live in device memory so that a captured CUDA graph stays valid
     const double t = (double)dyn[1];
     step_size = (float)((double)dyn[0] / (1.0 - pow(b1d, t)));
@@ -575,7 +596,7 @@ static int lm_grid(long long work, int threads) {
 
 GDN_API int gdn_absdiff_max(const float* a, const float* b, int64_t n, float* out_max, gdn_stream stream) {
   if (!a || !b || !out_max) return fail(GDN_INVALID_DESC, "gdn_absdiff_max: null pointer");
-  absdiff_max_kernel<<<lm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, reinterpret_cast<unsigned int*>(out_max));
+  GDN_CUDA_CHECK(launch_pdl(absdiff_max_kernel, dim3(lm_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream, 1, a, b, n, reinterpret_cast<unsigned int*>(out_max)));
   GDN_LAUNCH_CHECK("absdiff_max_kernel");
   return GDN_OK;
 }
@@ -594,28 +615,28 @@ GDN_API int gdn_loss(const gdn_loss_desc* d, gdn_stream stream) {
   k.inv_count = 1.0f / (float)((long long)d->n * d->h * d->w);
   k.sums = d->sums; k.dout = d->dout; k.dpre = d->dpre;
   k.grad_scale = d->grad_scale;
-  loss_kernel<<<lm_grid((long long)d->n * d->h * d->w, 256), 256, 0, (cudaStream_t)stream>>>(k);
+  GDN_CUDA_CHECK(launch_pdl(loss_kernel, dim3(lm_grid((long long)d->n * d->h * d->w, 256)), dim3(256), 0, (cudaStream_t)stream, 1, k));
   GDN_LAUNCH_CHECK("loss_kernel");
   return GDN_OK;
 }
 
 GDN_API int gdn_sqdiff_sum(const float* a, const float* b, int64_t n, double* out, gdn_stream stream) {
   if (!a || !b || !out || (n & 3)) return fail(GDN_INVALID_DESC, "gdn_sqdiff_sum: bad arguments (n must be a multiple of 4)");
-  sqdiff_sum_kernel<<<lm_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, out);
+  GDN_CUDA_CHECK(launch_pdl(sqdiff_sum_kernel, dim3(lm_grid(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, 1, a, b, n / 4, out));
   GDN_LAUNCH_CHECK("sqdiff_sum_kernel");
   return GDN_OK;
 }
 
 GDN_API int gdn_sqdiff_grad(const float* a, const float* b, int64_t n, float coef, float* grad, gdn_stream stream) {
   if (!a || !b || !grad || (n & 3)) return fail(GDN_INVALID_DESC, "gdn_sqdiff_grad: bad arguments (n must be a multiple of 4)");
-  sqdiff_grad_kernel<<<lm_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n / 4, coef, grad);
+  GDN_CUDA_CHECK(launch_pdl(sqdiff_grad_kernel, dim3(lm_grid(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, 1, a, b, n / 4, coef, grad));
   GDN_LAUNCH_CHECK("sqdiff_grad_kernel");
   return GDN_OK;
 }
 
 GDN_API int gdn_tanh_chain_add(const float* dout, const float* out, int64_t n, float scale, float* dpre, gdn_stream stream) {
   if (!dout || !out || !dpre || n < 0) return fail(GDN_INVALID_DESC, "gdn_tanh_chain_add: bad arguments");
-  tanh_chain_add_kernel<<<lm_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dout, out, n, scale, dpre);
+  GDN_CUDA_CHECK(launch_pdl(tanh_chain_add_kernel, dim3(lm_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream, 1, dout, out, n, scale, dpre));
   GDN_LAUNCH_CHECK("tanh_chain_add_kernel");
   return GDN_OK;
 }
@@ -644,9 +665,11 @@ GDN_API int gdn_depth_metrics(int variant, const float* gt_np, const float* gt, 
   m.out = out8;
   m.counts = reinterpret_cast<long long*>(counts);
   MetricImg* ws = reinterpret_cast<MetricImg*>(workspace);
-  if (variant == GDN_METRICS_KITTI) metrics_launch<0>(m, ws, (cudaStream_t)stream);
-  else if (variant == GDN_METRICS_NYU) metrics_launch<1>(m, ws, (cudaStream_t)stream);
-  else metrics_launch<2>(m, ws, (cudaStream_t)stream);
+  int lrc;
+  if (variant == GDN_METRICS_KITTI) lrc = metrics_launch<0>(m, ws, (cudaStream_t)stream);
+  else if (variant == GDN_METRICS_NYU) lrc = metrics_launch<1>(m, ws, (cudaStream_t)stream);
+  else lrc = metrics_launch<2>(m, ws, (cudaStream_t)stream);
+  if (lrc) return lrc;
   GDN_LAUNCH_CHECK("depth metrics kernels");
   return GDN_OK;
 }
@@ -666,21 +689,21 @@ GDN_API int gdn_adam_step(float* p, const float* g, float* m, float* v, int64_t 
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr / bc1);
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step_size, inv_sqrt_bc2, beta1,
-                                                                       beta2, eps, weight_decay, grad_scale, nullptr, 0.0, 0.0);
+  GDN_CUDA_CHECK(launch_pdl(adam_kernel, dim3(lm_grid(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, 1, p, g, m, v, n, step_size, inv_sqrt_bc2, beta1, beta2, eps, weight_decay, grad_scale, nullptr, 0.0, 0.0));
   GDN_LAUNCH_CHECK("adam_kernel");
   return GDN_OK;
 }
 
-__global__ void adam_tick_kernel(float* dyn) { dyn[1] += 1.0f; }
+__global__ void adam_tick_kernel(float* dyn) {
+  pdl_trigger();
+  pdl_wait(); dyn[1] += 1.0f; }
 
 GDN_API int gdn_adam_step_dyn(float* p, const float* g, float* m, float* v, int64_t n, float* dyn, double beta1,
                               double beta2, float eps, float weight_decay, float grad_scale, gdn_stream stream) {
   if (!p || !g || !m || !v || !dyn || n < 0) return fail(GDN_INVALID_DESC, "gdn_adam_step_dyn: bad arguments");
   if (n == 0) return GDN_OK;
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dyn);
-  adam_kernel<<<lm_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, 0.f, (float)beta1, (float)beta2,
-                                                                       eps, weight_decay, grad_scale, dyn, beta1, beta2);
+  GDN_CUDA_CHECK(launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, 1, dyn));
+  GDN_CUDA_CHECK(launch_pdl(adam_kernel, dim3(lm_grid(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, 1, p, g, m, v, n, 0.f, 0.f, (float)beta1, (float)beta2, eps, weight_decay, grad_scale, dyn, beta1, beta2));
   GDN_LAUNCH_CHECK("adam_kernel");
   return GDN_OK;
 }

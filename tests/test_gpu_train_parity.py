@@ -21,9 +21,29 @@ B, H, W = 4, 128, 416
 _STATE = {}
 
 
+def _conditioning(name, sd):
+    """bf16-operand emulation of the reference vs the fp32 reference on the test input: how much ANY implementation with
+    bf16 operands is expected to differ in this weight state"""
+    from oracle import model as OM
+    x = PP.inputs_for(name, B, H, W, 3)
+    with torch.no_grad():
+        r32 = OM.FORWARDS[name]({k: v.clone() for k, v in sd.items()}, x, istrain=False, train=True)
+        r16 = OM.FORWARDS[name]({k: v.clone() for k, v in sd.items()}, x, istrain=False, train=True, bf16=True)
+    return relerr(r16, r32)
+
+
 def _warm(name):
+    """the warm weight state, built once per network.  The precondition of every test below is that the state is well
+    conditioned (emulation vs fp32 <= 3e-2); the warm-up is deterministic (parity_probe.no_tf32), and should a software
+    stack land on a worse state it is trained further (10 more reference steps, at most 3 times) before the tests give up"""
     if name not in _STATE:
-        _STATE[name] = PP.state(name, "warm", B, H, W)
+        PP.no_tf32()
+        sd = PP.state(name, "warm", B, H, W)
+        for _ in range(3):
+            if _conditioning(name, sd) <= 3e-2:
+                break
+            sd = PP.warm_up(name, {k: v.detach().clone() for k, v in sd.items()}, B, H, W, steps=10)
+        _STATE[name] = sd
     return {k: v.clone() for k, v in _STATE[name].items()}
 
 
