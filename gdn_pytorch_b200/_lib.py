@@ -37,6 +37,7 @@ class WgradDesc(C.Structure):
         ("x0", Act), ("x1", Act), ("dy", Act), ("dw", C.c_void_p),
         ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("off_y", C.c_int32), ("off_x", C.c_int32),
         ("out_h", C.c_int32), ("out_w", C.c_int32), ("cout_pad", C.c_int32),
+        ("slabs", C.c_void_p), ("max_slabs", C.c_int32), ("splits_used", C.POINTER(C.c_int32)),
     ]
 
 

@@ -46,6 +46,23 @@ bool pdl_enabled() {
   return on;
 }
 
+bool det_enabled() {
+  // GDN_DETERMINISTIC=1 (read once): run-to-run reproducible training.  The default build reduces in fp32 with atomics in
+  // three places -- BatchNorm statistics (shared-memory atomics of the epilogue warps / of the reduce kernels' threads),
+  // and the split-K flush of the weight gradients (red.global.add.f32) -- whose order varies between runs (1e-7 relative,
+  // which a train-mode network at random init amplifies to ~3e-4 in the first loss, tools/check_repro.py).  In this mode
+  // the contributions are added in a fixed order instead: epilogue warps / thread replicas take turns (named barriers),
+  // every split of a weight gradient stores its partial tile to its own slab and gdn_unpack_wgrad sums the slabs in order.
+  // The remaining atomics are exact or order-independent: integer histograms and maxima, and fp64 sums of per-CTA fp32
+  // partials (24-bit addends in a 53-bit accumulator: exact unless the partials span more than ~2^15 in magnitude, and
+  // then only the last bit of a double that is rounded to float right after).
+  static const bool on = [] {
+    const char* e = getenv("GDN_DETERMINISTIC");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -96,6 +113,7 @@ extern "C" {
 GDN_API const char* gdn_last_error(void) { return gdn::g_err; }
 GDN_API int gdn_version(void) { return 100; }
 GDN_API int gdn_sm_count(void) { return gdn::device_sm_count(); }
+GDN_API int gdn_deterministic(void) { return gdn::det_enabled() ? 1 : 0; }
 }
 
 // ---- entry-point names of the coverage contract ------------------------------------------------

@@ -37,6 +37,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 bool pdl_enabled();
+// GDN_DETERMINISTIC=1: every fp32 reduction runs in a fixed order (see det_enabled() in common.cu)
+bool det_enabled();
 
 // Launch `kern` (which MUST execute pdl_wait()) on `st`, optionally as clusters of `cluster_x` CTAs.
 template <typename... P, typename... A>

@@ -8,6 +8,13 @@
 //   warp  7    MMA issuer 1: when a tile has J >= 2 sub-tiles the two issuers split them (disjoint accumulators).
 //              One issuer alone is instruction-latency bound (~70 cycles per MMA measured with ncu source
 //              counters against the 48 / 64 cycles an N = 64 / 128 MMA needs), two are not.
+//   warps 8-11 (template EW = 8 only) second epilogue group: the same tensor-memory lanes as warps 0-3 (a warp reaches
+//              lanes 32*(warp % 4) ...), the other half of the 32-column groups.  Why: with ONE warp per scheduler the
+//              epilogue runs at ~5 cycles per instruction (every instruction waits for its predecessor; ncu source
+//              counters of the 1x1 convolutions, profiles/r02l_ncu_conv1x1.txt: ~530 instructions = 2 900 cycles per
+//              32-column group with the BatchNorm statistics), so every launch whose reduction is shorter than that
+//              (K = Cin*kh*kw < ~2 900: 1x1, stride-2, im2col'd and head layers) is epilogue-bound.  A second warp per
+//              scheduler hides the dependency stalls.  Picked per layer by the caller's autotuner (bit 28 of algo).
 //
 // GEMM view: D[pixels(128), Cout tile(BN)] += A[pixels, 64 ch] * W[tap][Cout tile, 64 ch]^T over taps x 64-ch chunks.
 //
@@ -35,7 +42,7 @@
 
 namespace gdn {
 
-constexpr int kThreads = 8 * 32;
+
 constexpr int kWarpA = 4, kWarpMMA = 5, kWarpB = 6, kWarpMMA2 = 7;
 constexpr int kMaxA = 8, kMaxB = 8;
 
@@ -73,6 +80,7 @@ struct ConvK {
   int ksplit;
   float* ws;
   size_t ws_slab;
+  int det;                   // GDN_DETERMINISTIC: fixed-order accumulation of the per-CTA statistics
 };
 
 struct Ring {
@@ -92,11 +100,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   // saturate instead of overflowing to inf: a pre-BatchNorm value beyond +-65504 (possible with loaded checkpoints or
-  // huge fan-in) must stay finite through the normalisation that follows (the reference keeps it in fp32)
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 t = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+  // huge fan-in) must stay finite through the normalisation that follows (the reference keeps it in fp32).  One
+  // F2FP.SATFINITE per pair (round to nearest, then clamp to the largest finite half) instead of four FMNMX + a convert.
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 // Sum v[0..NV) over the 32 lanes; afterwards lane l holds the total of element l (valid for l < NV).
@@ -123,8 +131,8 @@ __device__ __forceinline__ float lane_transpose_sum(float (&v)[NV], int lane) {
   return v[0];
 }
 
-template <int BN, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int CG, int EW>
+__global__ void __launch_bounds__((4 + EW) * 32, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvK p) {
   extern __shared__ uint8_t smem_raw[];
@@ -157,11 +165,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&acc_full[i], p.nmma);
-      mbar_init(&acc_empty[i], 4 * CG);   // pair: the epilogue warps of both CTAs release the leader's accumulators
+      mbar_init(&acc_empty[i], EW * CG);  // pair: the epilogue warps of both CTAs release the leader's accumulators
     }
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 2 * (BN >= 32 ? BN : 32); i += kThreads) (&s_stat[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * (BN >= 32 ? BN : 32); i += (4 + EW) * 32) (&s_stat[0][0])[i] = 0.f;
   __syncwarp();
   if (warp == kWarpMMA) {
     if (CG == 2) {
@@ -359,10 +367,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 0..3
+    // ------------------------------------------------------------------ epilogue warps 0..3 (and 8..11 when EW = 8)
     constexpr int CW = BN >= 32 ? 32 : 16;  // columns per TMEM load
+    constexpr int ET = EW * 32;             // epilogue threads
     Ring rc;
-    const int q = warp;
+    const int q = warp & 3;                 // tensor-memory lane quarter this warp can read
+    const int half = warp >> 3;             // second group: the odd 32-column groups
+    const int et = (q + 4 * half) * 32 + lane;
     const int m = q * 32 + lane;
     const bool do_bstats = p.bs_raw != nullptr;                  // sum g, sum g*xhat of the masked total gradient
     const bool do_stats = p.stat_sum != nullptr && !do_bstats;   // forward: sum x, sum x^2 of the raw accumulators
@@ -403,7 +414,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         const int Hp = p.dst_h + 2 * p.ob_pad, Wp = p.dst_w + 2 * p.ob_pad;
 #pragma unroll 1
-        for (int cc = 0; cc < BN; cc += CW) {
+        for (int cc = half * CW; cc < BN; cc += (EW / 4) * CW) {
           float v[CW];
           {
             uint32_t r[CW];
@@ -434,9 +445,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
             const float t1 = lane_transpose_sum<CW>(s1, lane);
             const float t2 = lane_transpose_sum<CW>(s2, lane);
-            if (lane < CW) {
-              atomicAdd(&s_stat[0][cc + lane], t1);
-              atomicAdd(&s_stat[1][cc + lane], t2);
+            if (!p.det) {
+              if (lane < CW) {
+                atomicAdd(&s_stat[0][cc + lane], t1);
+                atomicAdd(&s_stat[1][cc + lane], t2);
+              }
+            } else {
+              // fixed order: the epilogue warps that share this column group take turns (all of them run this loop
+              // the same number of times: the conditions around it are uniform over the CTA)
+              for (int w = 0; w < 4; w++) {
+                if (q == w && lane < CW) {
+                  s_stat[0][cc + lane] += t1;
+                  s_stat[1][cc + lane] += t2;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+              }
             }
           }
           const bool full = (cb + CW <= p.cout);
@@ -500,8 +523,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int i = 0; i < CW; i++) s1[i] = valid ? v[i] : 0.f;
               const float t1 = lane_transpose_sum<CW>(s1, lane);
               const float t2 = lane_transpose_sum<CW>(s2, lane);
-              atomicAdd(&s_stat[0][cc + lane], t1);
-              atomicAdd(&s_stat[1][cc + lane], t2);
+              if (!p.det) {
+                atomicAdd(&s_stat[0][cc + lane], t1);
+                atomicAdd(&s_stat[1][cc + lane], t2);
+              } else {
+                for (int w = 0; w < 4; w++) {
+                  if (q == w) {
+                    s_stat[0][cc + lane] += t1;
+                    s_stat[1][cc + lane] += t2;
+                  }
+                  asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+                }
+              }
             }
           }
           if (valid) {
@@ -552,20 +585,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       rc.next(p.acc_bufs);
       if (any_stats && p.cout_blocks > 1) {
-        // the channel block changes from tile to tile: flush the per-CTA partials now (4 epilogue warps only)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = threadIdx.x; i < BN; i += 128) {
+        // the channel block changes from tile to tile: flush the per-CTA partials now (epilogue warps only)
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+        for (int i = et; i < BN; i += ET) {
           atomicAdd(p.stat_sum + nblk * BN + i, (double)s_stat[0][i]);
           atomicAdd(p.stat_sq + nblk * BN + i, (double)s_stat[1][i]);
           s_stat[0][i] = 0.f;
           s_stat[1][i] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
       }
     }
     if (any_stats && p.cout_blocks == 1) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x; i < BN; i += 128) {
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      for (int i = et; i < BN; i += ET) {
         if (i < p.cout) {
           atomicAdd(p.stat_sum + i, (double)s_stat[0][i]);
           atomicAdd(p.stat_sq + i, (double)s_stat[1][i]);
@@ -605,6 +638,7 @@ struct CombK {
   const __half* bs_raw;
   const float4* bs_coef;
   int bs_relu;
+  int det;
 };
 
 __global__ void __launch_bounds__(256) conv_splitk_combine_kernel(const CombK k) {
@@ -683,10 +717,24 @@ __global__ void __launch_bounds__(256) conv_splitk_combine_kernel(const CombK k)
     }
   }
   if (k.stat_sum) {
+    if (!k.det) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      atomicAdd(&s_red[c8 + j], s1[j]);
-      atomicAdd(&s_red[k.C + c8 + j], s2[j]);
+      for (int j = 0; j < 8; j++) {
+        atomicAdd(&s_red[c8 + j], s1[j]);
+        atomicAdd(&s_red[k.C + c8 + j], s2[j]);
+      }
+    } else {
+      // fixed order: the blockDim.x / cg threads that hold the same 8 channels take turns
+      for (int r = 0; r < (int)blockDim.x / cg; r++) {
+        if ((int)threadIdx.x / cg == r) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            s_red[c8 + j] += s1[j];
+            s_red[k.C + c8 + j] += s2[j];
+          }
+        }
+        __syncthreads();
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < k.C; i += blockDim.x) {
@@ -717,19 +765,19 @@ static int make_act_map(CUtensorMap* tm, const gdn_act& a, int stride, const uin
   return encode_tmap_bf16(tm, a.ptr, 5, dims, str, box);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int EW>
 static int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvK& k, size_t smem,
                   cudaStream_t st) {
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    GDN_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
     configured[dev] = true;
   }
   const int slots = device_sm_count() / CG;   // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int units = k.total_tiles < slots ? k.total_tiles : slots;
-  GDN_CUDA_CHECK(launch_pdl(conv_igemm_kernel<BN, CG>, dim3(units * CG), dim3(kThreads), smem, st, CG, a0, a1, b, k));
+  GDN_CUDA_CHECK(launch_pdl(conv_igemm_kernel<BN, CG, EW>, dim3(units * CG), dim3((4 + EW) * 32), smem, st, CG, a0, a1, b, k));
   GDN_LAUNCH_CHECK("conv_igemm_kernel");
   return GDN_OK;
 }
@@ -833,6 +881,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
                   (size_t)d->workspace_bytes);
   }
   k.ksplit = ksplit;
+  k.det = det_enabled() ? 1 : 0;
   k.ws = reinterpret_cast<float*>(d->workspace);
   k.ws_slab = (size_t)d->src0.n * d->out_h * d->out_w * d->cout;
   const int j_req = (d->algo >> 8) & 0xff;  // HALO: sub-tiles per tile requested by the caller's autotuner (0 = heuristic)
@@ -884,6 +933,17 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   } else {
     int tw = 8;
     while (tw > d->out_w && tw > 1) tw >>= 1;
+    if (taps == 1 && d->stride == 1 && d->out_w >= 16) {
+      // 1x1 convolutions need no 2-D locality: make the 128-pixel tile as WIDE as the row allows without padding it
+      // (416 columns: 4 rows x 32 pixels), so that every TMA row and every warp-wide store is one contiguous run of
+      // 32 pixels instead of 8 -- these launches are bound by HBM / the epilogue, not by the MMAs
+      int best = tw, best_cols = (d->out_w + tw - 1) / tw * tw;
+      for (int c = 16; c <= 128 && c <= d->out_w; c <<= 1) {
+        const int cols = (d->out_w + c - 1) / c * c;
+        if (cols <= best_cols) { best = c; best_cols = cols; }
+      }
+      tw = best;
+    }
     int th = 128 / tw;
     while (th / 2 >= d->out_h && th > 1) th >>= 1;
     int nb = 128 / (tw * th);
@@ -922,18 +982,20 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   const size_t smem = (size_t)k.na * k.a_bytes + (size_t)k.nbst * b_bytes + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   k.total_tiles *= k.ksplit;
+  // bit 28 of algo: second epilogue warp group (8 epilogue warps) -- for launches with a short reduction
+  const bool ew8 = ((d->algo >> 28) & 1) && BN >= 64;
   if (cg == 2) {
     switch (BN) {
-      case 64: rc = launch<64, 2>(tmA0, tmA1, tmB, k, smem, st); break;
-      case 128: rc = launch<128, 2>(tmA0, tmA1, tmB, k, smem, st); break;
-      default: rc = launch<256, 2>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 64: rc = ew8 ? launch<64, 2, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<64, 2, 4>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 128: rc = ew8 ? launch<128, 2, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<128, 2, 4>(tmA0, tmA1, tmB, k, smem, st); break;
+      default: rc = ew8 ? launch<256, 2, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<256, 2, 4>(tmA0, tmA1, tmB, k, smem, st); break;
     }
   } else {
     switch (BN) {
-      case 16: rc = launch<16, 1>(tmA0, tmA1, tmB, k, smem, st); break;
-      case 64: rc = launch<64, 1>(tmA0, tmA1, tmB, k, smem, st); break;
-      case 128: rc = launch<128, 1>(tmA0, tmA1, tmB, k, smem, st); break;
-      default: rc = launch<256, 1>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 16: rc = launch<16, 1, 4>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 64: rc = ew8 ? launch<64, 1, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<64, 1, 4>(tmA0, tmA1, tmB, k, smem, st); break;
+      case 128: rc = ew8 ? launch<128, 1, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<128, 1, 4>(tmA0, tmA1, tmB, k, smem, st); break;
+      default: rc = ew8 ? launch<256, 1, 8>(tmA0, tmA1, tmB, k, smem, st) : launch<256, 1, 4>(tmA0, tmA1, tmB, k, smem, st); break;
     }
   }
   if (rc || k.ksplit == 1) return rc;
@@ -945,6 +1007,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   c.out16 = d->out_bf16.ptr; c.half = d->out16_is_half;
   c.stat_sum = d->stat_sum; c.stat_sq = d->stat_sqsum;
   c.bs_raw = k.bs_raw; c.bs_coef = k.bs_coef; c.bs_relu = k.bs_relu;
+  c.det = k.det;
   const long long items = c.npix * (c.C / 8);
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)device_sm_count() * 4;

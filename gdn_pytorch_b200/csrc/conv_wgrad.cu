@@ -47,6 +47,7 @@ struct WgK {
   int cin_total, cout_pad;
   int kw;
   float* dw;
+  size_t det_slab;   // 0: splits add to dw with red.global.add; else split s stores to dw + s*det_slab (floats)
   WgUnit units[kMaxUnits];
 };
 
@@ -303,18 +304,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constan
           const int chunk = halo ? cic : (second ? un.cB : un.cA);
           const int ci = chunk * 64 + (m & 63);
           const int tap = r * p.kw + s;
-          float* dst = p.dw + ((size_t)tap * p.cin_total + ci) * p.cout_pad + cob * WN;
+          // deterministic mode: split sp owns slab sp of the gradient and stores to it (no atomics)
+          float* dst = p.dw + (size_t)(w % p.splits) * p.det_slab + ((size_t)tap * p.cin_total + ci) * p.cout_pad + cob * WN;
 #pragma unroll 1
           for (int cc = 0; cc < WN; cc += 32) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((u - u0) * WN + cc), v);
             tmem_ld_wait();
             if (live) {
+              if (p.det_slab) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + i), "r"(v[i]), "r"(v[i + 1]),
-                             "r"(v[i + 2]), "r"(v[i + 3])
-                             : "memory");
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<uint4*>(dst + cc + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + i), "r"(v[i]), "r"(v[i + 1]),
+                               "r"(v[i + 2]), "r"(v[i + 3])
+                               : "memory");
+              }
             }
           }
         }
@@ -384,6 +392,7 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
   k.cout_pad = d->cout_pad;
   k.kw = d->kw;
   k.dw = d->dw;
+  k.det_slab = 0;
   k.co_blocks = d->cout_pad / WN;
   const int upc_max = 512 / WN;           // units per CTA (tensor memory columns)
 
@@ -485,6 +494,15 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d_wgrad(const gdn
   int splits = sms / items;
   if (splits < 1) splits = 1;
   if (splits > k.total_pt) splits = k.total_pt;
+  if (d->slabs) {
+    // deterministic split-K: every split stores its partial gradient to its own slab (each split holds >= 1 pixel tile,
+    // so every slab is written completely); gdn_unpack_wgrad_slabs sums them in order
+    if (d->max_slabs < 1 || !d->splits_used) return fail(GDN_INVALID_DESC, "gdn_conv2d_wgrad: slabs need max_slabs >= 1 and splits_used");
+    if (splits > d->max_slabs) splits = d->max_slabs;
+    k.dw = d->slabs;
+    k.det_slab = (size_t)taps * k.cin_total * k.cout_pad;
+    *d->splits_used = splits;
+  }
   k.splits = splits;
   k.total_work = items * splits;
   {

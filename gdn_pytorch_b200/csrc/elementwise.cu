@@ -604,6 +604,7 @@ struct BnBwd {
   float* dbeta;                   // += sum_g
   int raw_half;
   int dact_bf16;                  // dact holds bf16 (written by a convolution epilogue with the ReLU mask already applied)
+  int det;                        // GDN_DETERMINISTIC: thread replicas add their partials in a fixed order
 };
 
 // 8 consecutive gradient values of element offset `off` (fp32 stream, or the bf16 buffer a dgrad epilogue wrote)
@@ -657,10 +658,25 @@ __global__ void bn_bwd_reduce_kernel(const BnBwd b) {
         sx[j] += gq * (x[j] - mu[j]) * rs[j];
       }
     }
+    if (!b.det) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      atomicAdd(&s_red[c8 + j], sg[j]);
-      atomicAdd(&s_red[b.C + c8 + j], sx[j]);
+      for (int j = 0; j < 8; j++) {
+        atomicAdd(&s_red[c8 + j], sg[j]);
+        atomicAdd(&s_red[b.C + c8 + j], sx[j]);
+      }
+    }
+  }
+  if (b.det) {
+    // fixed order: the pixel lanes that hold the same 8 channels take turns
+    for (int r = 0; r < lanes; r++) {
+      if (pl == r) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s_red[g * 8 + j] += sg[j];
+          s_red[b.C + g * 8 + j] += sx[j];
+        }
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
@@ -771,10 +787,24 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const
       }
     }
   }
+  if (!b.det) {
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    atomicAdd(&s_red[c8 + j], sg[j]);
-    atomicAdd(&s_red[b.C + c8 + j], (sx[j] - b.mean[c8 + j] * sg[j]) * b.rstd[c8 + j]);
+    for (int j = 0; j < 8; j++) {
+      atomicAdd(&s_red[c8 + j], sg[j]);
+      atomicAdd(&s_red[b.C + c8 + j], (sx[j] - b.mean[c8 + j] * sg[j]) * b.rstd[c8 + j]);
+    }
+  } else {
+    // fixed order: the kEwThreads >> lg_cg threads that hold the same 8 channels take turns
+    for (int r = 0; r < (kEwThreads >> lg_cg); r++) {
+      if ((int)(threadIdx.x >> lg_cg) == r) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          s_red[c8 + j] += sg[j];
+          s_red[b.C + c8 + j] += (sx[j] - b.mean[c8 + j] * sg[j]) * b.rstd[c8 + j];
+        }
+      }
+      __syncthreads();
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < b.C; i += blockDim.x) {
@@ -1026,7 +1056,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
 }
 
 // grad[w index] (+)= packed_dw[t][b][a]   (wgrad layout: [tap][ci = b][co = a], co padded to Apad)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k, int accumulate) {
+// (both unpack kernels: `slabs` > 1 = the deterministic split-K layout -- slab s of the weight gradient lies slab_elems
+// floats after slab s - 1; the slabs are summed in index order)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k, int accumulate,
+                                    const int slabs, const long long slab_elems) {
   pdl_trigger();
   pdl_wait();
   const int T = k.col_c ? 1 : k.kh * k.kw;
@@ -1047,7 +1080,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
       if (k.flip) { r = k.kh - 1 - r; s = k.kw - 1 - s; }
       widx = a * k.sa + b * k.sb + r * k.sr + s * k.ss;
     }
-    const float v = dw[((long long)t * k.Bpad + b) * k.Apad + a];
+    const float* src = dw + ((long long)t * k.Bpad + b) * k.Apad + a;
+    float v = src[0];
+    for (int sl = 1; sl < slabs; sl++) v += src[(long long)sl * slab_elems];
     if (accumulate) grad[widx] += v; else grad[widx] = v;
   }
 }
@@ -1105,7 +1140,7 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const PackJob* __restri
 
 // grad[a*sa + b*sb + tap] (+)= dw[t][b][a]
 __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restrict__ dw, float* __restrict__ grad, const PackK k,
-                                                         int accumulate) {
+                                                         int accumulate, const int slabs, const long long slab_elems) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_tile[];
@@ -1115,7 +1150,11 @@ __global__ void __launch_bounds__(256) unpack_tile_kernel(const float* __restric
     const int al = i & (kPackTile - 1), bl = (i >> 4) & (kPackTile - 1), t = i >> 8;
     const int a = a0 + al, b = b0 + bl;
     float v = 0.f;
-    if (a < k.A && b < k.B) v = __ldg(dw + ((long long)t * k.Bpad + b) * k.Apad + a);
+    if (a < k.A && b < k.B) {
+      const float* src = dw + ((long long)t * k.Bpad + b) * k.Apad + a;
+      v = __ldg(src);
+      for (int sl = 1; sl < slabs; sl++) v += __ldg(src + (long long)sl * slab_elems);
+    }
     const int tap = k.flip ? T - 1 - t : t;
     s_tile[(al * kPackTile + bl) * (T + 1) + tap] = v;
   }
@@ -1278,6 +1317,7 @@ static int fill_bnbwd(const gdn_bn_bwd_desc* d, BnBwd& b) {
   b.dgamma = d->dgamma; b.dbeta = d->dbeta;
   b.raw_half = d->raw_is_half;
   b.dact_bf16 = d->dact_is_bf16;
+  b.det = det_enabled() ? 1 : 0;
   return GDN_OK;
 }
 
@@ -1462,8 +1502,17 @@ GDN_API int gdn_pack_weights_table(const void* jobs_dev, int njobs, int total_ct
   return GDN_OK;
 }
 
+GDN_API int gdn_unpack_wgrad_slabs(const gdn_pack_desc* d, const float* dw, int slabs, int64_t slab_elems, float* grad,
+                                   int accumulate, gdn_stream stream);
 GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* grad, int accumulate, gdn_stream stream) {
+  return gdn_unpack_wgrad_slabs(d, dw, 1, 0, grad, accumulate, stream);
+}
+
+GDN_API int gdn_unpack_wgrad_slabs(const gdn_pack_desc* d, const float* dw, int slabs, int64_t slab_elems, float* grad,
+                                   int accumulate, gdn_stream stream) {
   if (!d || !dw || !grad) return fail(GDN_INVALID_DESC, "gdn_unpack_wgrad: null pointer");
+  if (slabs < 1 || (slabs > 1 && slab_elems <= 0)) return fail(GDN_INVALID_DESC, "gdn_unpack_wgrad: %d slabs of %lld floats", slabs, (long long)slab_elems);
+  const long long se = (long long)slab_elems;
   PackK k;
   fill_pack(d, k);
   if (pack_tileable(k)) {
@@ -1477,12 +1526,12 @@ GDN_API int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* gra
       configured[dev] = true;
     }
     dim3 grid((k.B + kPackTile - 1) / kPackTile, (k.A + kPackTile - 1) / kPackTile);
-    GDN_CUDA_CHECK(launch_pdl(unpack_tile_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 1, dw, grad, k, accumulate));
+    GDN_CUDA_CHECK(launch_pdl(unpack_tile_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 1, dw, grad, k, accumulate, slabs, se));
     GDN_LAUNCH_CHECK("unpack_tile_kernel");
     return GDN_OK;
   }
   const long long work = (long long)(k.col_c ? 1 : k.kh * k.kw) * k.A * k.B;
-  GDN_CUDA_CHECK(launch_pdl(unpack_wgrad_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, dw, grad, k, accumulate));
+  GDN_CUDA_CHECK(launch_pdl(unpack_wgrad_kernel, dim3(ew_grid(work)), dim3(kEwThreads), 0, (cudaStream_t)stream, 1, dw, grad, k, accumulate, slabs, se));
   GDN_LAUNCH_CHECK("unpack_wgrad_kernel");
   return GDN_OK;
 }

@@ -84,6 +84,9 @@ class Engine:
         parameter gradients): the caller writes dL/d(t) into ``dact[t]`` for every t in grad_seeds, run_backward()
         propagates them (input_grad=True: down to ``dact["in"]``, also for thin 1-channel inputs)."""
         self.L = _lib.lib()
+        # GDN_DETERMINISTIC=1 (read once by the library): fixed-order fp32 reductions; the engine's part is the slab
+        # workspace of the split-K weight gradients (include/gdn_b200.h, gdn_wgrad_desc.slabs)
+        self.det = bool(self.L.gdn_deterministic())
         self.g, self.P, self.N, self.H, self.W = graph, params, N, H, W
         self.train, self.do_bwd = train, backward
         self.frozen_bwd = backward and not train
@@ -120,7 +123,9 @@ class Engine:
                 self.pack_ops_bwd = self._batch_packs(self.pack_ops_bwd)
         self._wversion = None
         self.timeline, self.tl_tag = None, "fwd"
-        if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+        # (deterministic mode keeps the library heuristics: a variant picked by TIME may differ between two runs, and the
+        # staging variants group the pixels differently, i.e. sum the BatchNorm statistics in a different fp32 order)
+        if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not self.det and not torch.cuda.is_current_stream_capturing():
             self.autotune()
 
     # ------------------------------------------------------------------ shapes
@@ -341,6 +346,10 @@ class Engine:
             thin = u.cin < 64
             cu.thin = thin
             kk = k * k
+            if (u.cout == 1 and not thin and k == 9 and stride == 1 and len(u.srcs) == 1 and not u.up and u.bn is None
+                    and not u.reflect and u.resid is None and u.cin % 64 == 0 and os.environ.get("GDN_HEAD_TAPS", "1") != "0"):
+                self._build_head_forward(u, cu, wt, flip)
+                continue
             # ---------------- weights (forward pack)
             if thin:
                 kpad = _round_up(kk * u.cin, 64)
@@ -508,6 +517,55 @@ class Engine:
                     self.launches_fwd += 1
                 if (direct[1:] or derived) and not self.need_f32[u.out]:
                     raise AssertionError("variant derivation needs the fp32 copy of " + u.out)
+
+    def _build_head_forward(self, u, cu, wt, flip):
+        """64 -> 1 head (k9, zero pad 4, tanh; AE_model_unet.py:300,362 / :521,570).  As a convolution it has ONE output
+        channel: a 16-wide MMA tile whose 81 taps each re-read the activation window from shared memory (0.53 ms at
+        21 TFLOP/s, profiles/r02f_profile_ops.log).  Here the taps are the N dimension of one 1x1 convolution,
+        Z[p][t] = <x[p], w[t]> (fp16, 128 columns), and gdn_head_gather sums Z over the 9x9 neighbourhood and applies tanh."""
+        L, N, dev = self.L, self.N, self.dev
+        k, kk, ho, wo = cu.k, cu.k * cu.k, cu.ho, cu.wo
+        zc = _round_up(kk, 64)
+        cu.cout_pad = zc
+        cu.wf = torch.empty((1, zc, u.cin), dtype=torch.bfloat16, device=dev)
+        # W[t][c]: Conv2d weight [1][c][r][s] and ConvTranspose2d weight [c][1][r][s] are both c*kk + tap in memory; the
+        # transposed head is a convolution with the flipped kernel (tap kk-1-t)
+        if flip:
+            pd, w_off = PackDesc(1, 1, kk, u.cin, zc, u.cin, -1, kk, 0, 0, 0, 0), kk - 1
+        else:
+            pd, w_off = PackDesc(1, 1, kk, u.cin, zc, u.cin, 1, kk, 0, 0, 0, 0), 0
+        cu.pd_fwd = pd
+        op = self._pack_call(pd, wt, None, cu.wf, "pack " + u.conv, w_off=w_off)
+        op.cu = cu
+        self.pack_ops.append(op)
+        cu.z = torch.empty((N, ho, wo, zc), dtype=torch.float16, device=dev)
+        d = ConvDesc()
+        d.src0 = self._act_struct(u.srcs[0], self._variant(u))
+        d.kh = d.kw = 1
+        d.stride = 1
+        d.off_y = d.off_x = 0
+        d.weights = cu.wf.data_ptr()
+        d.out_h, d.out_w = ho, wo
+        d.cout = d.cout_pad = zc
+        d.algo = 0
+        d.dst_h, d.dst_w = ho, wo
+        d.dst_sy = d.dst_sx = 1
+        d.out_bf16 = Act(cu.z.data_ptr(), N, ho, wo, zc, 0)
+        d.out16_is_half = 1
+        cu.conv_desc = d
+        cu.fwd_conv_idx = len(self.fwd)
+        self.fwd.append(self._call(L.gdn_conv2d, d, "conv " + u.conv))
+        out = self.f32[u.out]
+        pad_exec, tanh = -cu.off, int(u.tanh)
+
+        def gather(s, cu=cu, out=out):
+            rc = L.gdn_head_gather(C.c_void_p(cu.z.data_ptr()), 1, zc, N, ho, wo, k, pad_exec, tanh,
+                                   C.c_void_p(out.data_ptr()), s)
+            if rc:
+                _lib.check(rc, "head_gather " + u.conv)
+        gather.label = "head-gather " + u.conv
+        self.fwd.append(gather)
+        self.launches_fwd += 2
 
     def _resolve_first_use(self):
         """index of the forward op that first reads each weight pack (for packs issued on the side stream)"""
@@ -769,9 +827,10 @@ class Engine:
             wd.kh, wd.kw, wd.stride = fd.kh, fd.kw, fd.stride
             wd.off_y, wd.off_x = fd.off_y, fd.off_x
             wd.out_h, wd.out_w, wd.cout_pad = ho, wo, u.cout
+            used = self._det_slabs(wd)
             zero_dw = lambda s, dw=dw: dw.zero_()
             zero_dw.label = "misc"
-            side_ops = [zero_dw, self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv)]
+            side_ops = ([] if used is not None else [zero_dw]) + [self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv)]
             if cu.thin:
                 up_ = PackDesc(k, k, u.cout, cu.kpad, u.cout, cu.kpad, u.cin * kk, kk, k, 1, 0, u.cin)
             elif u.transposed:
@@ -780,8 +839,12 @@ class Engine:
                 up_ = PackDesc(k, k, u.cout, u.cin, u.cout, u.cin, u.cin * kk, kk, k, 1, 0, 0)
             gbuf = self.grad[u.conv + ".weight"]
 
-            def unpack(s, up_=up_, dw=dw, gbuf=gbuf, name=u.conv):
-                rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr()), 1, s)
+            def unpack(s, up_=up_, dw=dw, gbuf=gbuf, name=u.conv, used=used):
+                if used is None:
+                    rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr()), 1, s)
+                else:       # deterministic split-K: sum the slabs the wgrad launch just filled, in index order
+                    rc = L.gdn_unpack_wgrad_slabs(C.byref(up_), C.c_void_p(self.dw_slabs.data_ptr()), used.value,
+                                                  C.c_int64(dw.numel()), C.c_void_p(gbuf.data_ptr()), 1, s)
                 if rc:
                     _lib.check(rc, "unpack " + name)
             unpack.label = "unpack " + u.conv
@@ -1116,7 +1179,9 @@ class Engine:
         wd.kh = wd.kw = 1
         wd.stride = 1
         wd.out_h, wd.out_w, wd.cout_pad = ho, wo, kp
-        self.bwd.append(lambda s, dw=dw: dw.zero_())
+        used = self._det_slabs(wd)
+        if used is None:
+            self.bwd.append(lambda s, dw=dw: dw.zero_())
         self.bwd.append(self._call(L.gdn_conv2d_wgrad, wd, "wgrad head"))
         gbuf = self.grad[u.conv + ".weight"]
         # dw is [ci = c][co = t'] ; parameter is w[0][c][r][s] (conv, taps flipped) or w[c][0][r][s] (convT)
@@ -1128,13 +1193,34 @@ class Engine:
             goff = kk - 1
 
         def unpack(s):
-            rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr() + 4 * goff), 1, s)
+            if used is None:
+                rc = L.gdn_unpack_wgrad(C.byref(up_), C.c_void_p(dw.data_ptr()), C.c_void_p(gbuf.data_ptr() + 4 * goff), 1, s)
+            else:
+                rc = L.gdn_unpack_wgrad_slabs(C.byref(up_), C.c_void_p(self.dw_slabs.data_ptr()), used.value,
+                                              C.c_int64(dw.numel()), C.c_void_p(gbuf.data_ptr() + 4 * goff), 1, s)
             if rc:
                 _lib.check(rc, "unpack head")
         self.bwd.append(unpack)
         self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
         self.launches_bwd += 5
         cu.keep = [wdg]
+
+    _DET_MAX_SLABS = 32
+
+    def _det_slabs(self, wd):
+        """GDN_DETERMINISTIC=1: point a weight-gradient descriptor at the engine's slab workspace (every split of the
+        reduction stores its partial gradient to its own slab, the unpack sums them in order).  Returns the c_int32 the
+        library writes the number of splits to at every call, or None in the default (atomic) mode."""
+        if not self.det:
+            return None
+        if getattr(self, "dw_slabs", None) is None:
+            self.dw_slabs = torch.empty(self._DET_MAX_SLABS * self.dw_scratch.numel(), dtype=torch.float32, device=self.dev)
+        used = C.c_int32(0)
+        wd.slabs = self.dw_slabs.data_ptr()
+        wd.max_slabs = self._DET_MAX_SLABS
+        wd.splits_used = C.pointer(used)
+        self._keep_det = getattr(self, "_keep_det", []) + [used]
+        return used
 
     def _attach_splitk_workspace(self):
         """one fp32 scratch buffer per engine for split-K launches (maps with fewer pixel tiles than SMs): every
@@ -1241,8 +1327,9 @@ class Engine:
 
 # ------------------------------------------------------------------------------------------- conv autotuning
 # algo word of gdn_conv_desc: bits 0-7 mode (GDN_CONV_TAPBOX = 1, GDN_CONV_HALO = 2), bits 8-15 HALO sub-tiles J,
-# bits 16-23 output-channel tile / 64 (0 = widest), bit 24 CTA pairs (tcgen05 cta_group::2)
+# bits 16-23 output-channel tile / 64 (0 = widest), bit 24 CTA pairs (tcgen05 cta_group::2), bit 28 second epilogue warp group
 _PAIR = 1 << 24
+_EW8 = 1 << 28
 _ALGOS = (2 | (4 << 8), 2 | (2 << 8), 2 | (1 << 8), 1,
           2 | (4 << 8) | _PAIR, 2 | (2 << 8) | _PAIR, 2 | (1 << 8) | _PAIR, 1 | _PAIR)
 _S2, _S4 = 2 << 25, 4 << 25     # split-K over the input-channel chunks (needs the engine's workspace)
@@ -1261,7 +1348,13 @@ def autotune_conv(L, d, reps=3, what="conv"):
     # wide layers on small maps leave SMs idle with 256-channel tiles: let 128-wide tiles compete
     small = d.cout_pad >= 256 and d.src0.n * d.out_h * d.out_w * (d.cout_pad // 256) < 128 * 148 * 2
     split = _ALGOS_SPLIT if (d.workspace and d.src0.n * d.out_h * d.out_w <= 128 * 148) else ()
-    for algo in _ALGOS + (_ALGOS_NARROW if small else ()) + split:
+    cands = _ALGOS + (_ALGOS_NARROW if small else ()) + split
+    # launches with a short reduction are bound by their epilogue (one warp per scheduler: ~2 900 cycles per 32-column group
+    # against K = Cin*kh*kw cycles of MMAs): let the variants with eight epilogue warps compete there
+    kred = (d.src0.c + (d.src1.c if d.src1.ptr else 0)) * d.kh * d.kw
+    if kred <= 4096 and d.cout_pad >= 64 and os.environ.get("GDN_EW8", "1") != "0":
+        cands = cands + tuple(a | _EW8 for a in cands)
+    for algo in cands:
         if (algo & _PAIR) and not pairs_ok:
             continue
         d.algo = algo

@@ -12,6 +12,8 @@
  *   gdn_conv2d_wgrad      weight gradient of the same convolutions (autograd of the above)
  *   gdn_im2col            thin-channel layers (Cin = 1 / 3, Cout = 1) reshaped for the tensor-core path:
  *                         src/AE_model_unet.py:272 (3->64), :494 (1->64), :292/:521 (64->1 heads)
+ *   gdn_head_gather       second half of the 64 -> 1 heads (src/AE_model_unet.py:300,362 / :521,570): the 81 taps run as the
+ *                         N dimension of ONE 1x1 gdn_conv2d (Z[p][tap]), this sums Z over the 9x9 neighbourhood + tanh
  *   gdn_act_forward       nn.BatchNorm2d apply + nn.ReLU + residual add + nn.ReflectionPad2d + F.interpolate(x2):
  *                         src/AE_model_unet.py:51-57,66-69,86-87,135,336-355
  *   gdn_bn_finalize       batch statistics -> scale/shift, running-stat update (nn.BatchNorm2d training mode)
@@ -67,7 +69,8 @@ typedef struct {
   int32_t cout;              /* real output channels */
   int32_t cout_pad;          /* channels in the weight tensor (multiple of 16; == cout unless cout < 16) */
   int32_t algo;              /* GDN_CONV_* in the low byte; bits 8-15: HALO sub-tiles per tile (1, 2, 4), bits 16-23: output-channel
-                                tile / 64 (1, 2, 4); bit 24: CTA pairs; bits 25-27: split-K (see workspace);
+                                tile / 64 (1, 2, 4); bit 24: CTA pairs; bits 25-27: split-K (see workspace); bit 28: eight
+                                epilogue warps instead of four (launches with a short reduction are epilogue-bound);
                                 0 = library heuristic.  Every choice WITHOUT split-K produces bit-identical
                                 outputs (BN statistics aside: atomics); callers may time them. */
   /* epilogue */
@@ -110,6 +113,14 @@ typedef struct {
   gdn_act dy;                /* gradient of the conv output, interior = out_h x out_w, c = cout_pad */
   float* dw;                 /* fp32 [kh*kw][cin_total][cout_pad] (co fastest), accumulated into (caller zeroes) */
   int32_t kh, kw, stride, off_y, off_x, out_h, out_w, cout_pad;
+  /* Deterministic split-K (optional; the engine sets it under GDN_DETERMINISTIC=1).  The reduction over the pixels is
+   * split over the SMs; by default every split ADDS its partial gradient to dw with fp32 atomics (order varies from run
+   * to run).  With `slabs` set, split s STORES its partial to slabs + s * kh*kw*cin_total*cout_pad floats instead (dw is
+   * not touched, nothing needs zeroing), at most max_slabs splits are used, and their number is written to *splits_used
+   * (host memory, at call time).  gdn_unpack_wgrad_slabs sums the slabs in index order. */
+  float* slabs;
+  int32_t max_slabs;
+  int32_t* splits_used;
 } gdn_wgrad_desc;
 
 int gdn_conv2d_wgrad(const gdn_wgrad_desc* d, gdn_stream stream);
@@ -120,6 +131,13 @@ int gdn_conv2d_wgrad(const gdn_wgrad_desc* d, gdn_stream stream);
  * column k = (r*kw + s)*c + ch holds src[n][ch][y + r - pad][x + s - pad] (reflection or zero padding). */
 int gdn_im2col(const float* src, void* dst, int n, int c, int h, int w, int kh, int kw, int pad, int reflect,
                int kpad, gdn_stream stream);
+
+/* Single-output-channel k x k convolution with zero padding, given Z[p][t] = <x[p][:], w[t][:]> for every tap t = r*k + s
+ * (a 1x1 gdn_conv2d with the taps as output channels; z: [n][h][w][zc] fp16 (z_is_half) or bf16, zc % 8 == 0, zc >= k*k
+ * rounded up to 8):  out[n][y][x] = act( sum_{r,s} z[n][y + r - pad][x + s - pad][r*k + s] ), taps outside the image
+ * skipped (= zero padding of x), act = tanh when tanh_out.  Fixed summation order (r-major).  k = 9. */
+int gdn_head_gather(const void* z, int z_is_half, int zc, int n, int h, int w, int k, int pad, int tanh_out, float* out,
+                    gdn_stream stream);
 
 /* batch statistics -> per-channel scale = gamma*rstd, shift = beta - mean*scale; saves mean / rstd for backward;
  * updates running stats (momentum, unbiased variance) when running_mean != NULL.  coef4 (optional, 16-byte aligned
@@ -215,6 +233,10 @@ typedef struct {
 } gdn_pack_desc;
 int gdn_pack_weights(const gdn_pack_desc* d, const float* w, const float* scale_a, void* out, gdn_stream stream);
 int gdn_unpack_wgrad(const gdn_pack_desc* d, const float* dw, float* grad, int accumulate, gdn_stream stream);
+/* same, from `slabs` partial gradients lying slab_elems floats apart (deterministic split-K of gdn_conv2d_wgrad), summed in
+ * index order */
+int gdn_unpack_wgrad_slabs(const gdn_pack_desc* d, const float* dw, int slabs, int64_t slab_elems, float* grad, int accumulate,
+                           gdn_stream stream);
 /* Batched re-pack: every packed tensor of a network in ONE launch.  The caller builds a job table on the host with
  * gdn_pack_job_fill (entries of gdn_pack_job_size() bytes, cta0 = running sum of the n_ctas returned so far), copies
  * it to device memory once, and calls gdn_pack_weights_table after every optimizer step.  Non-tileable tensors
@@ -341,6 +363,8 @@ size_t gdn_workspace_bytes(const gdn_conv_desc* d);
 const char* gdn_last_error(void);
 int gdn_version(void);
 int gdn_sm_count(void);
+/* 1 when the library runs its fp32 reductions in a fixed order (environment GDN_DETERMINISTIC=1, read once) */
+int gdn_deterministic(void);
 
 #ifdef __cplusplus
 }

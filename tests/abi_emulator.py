@@ -6,7 +6,7 @@ reflection folds ...) does not depend on the GPU, so the CPU suite runs the plan
 implements the documented semantics of each entry point with torch CPU ops on the SAME descriptors (raw pointers
 into CPU tensors).  bf16 operand rounding is reproduced (operands are read from bf16 buffers), accumulation is fp32.
 
-Covered: gdn_bn_fold, gdn_bn_finalize, gdn_pack_weights, gdn_unpack_wgrad, gdn_im2col, gdn_conv2d, gdn_conv2d_wgrad,
+Covered: gdn_bn_fold, gdn_bn_finalize, gdn_pack_weights, gdn_unpack_wgrad, gdn_im2col, gdn_head_gather, gdn_conv2d, gdn_conv2d_wgrad,
 gdn_act_forward, gdn_bn_bwd_reduce, gdn_act_backward, gdn_act_backward_frozen, gdn_fold_grad, gdn_sqdiff_sum,
 gdn_sqdiff_grad, gdn_tanh_chain_add.  Loss, metrics, Adam and the image kernels are not emulated (they have direct
 GPU-vs-oracle tests).
@@ -75,6 +75,9 @@ class EmulatedLib:
     def _e_sm_count(self):
         return 148
 
+    def _e_deterministic(self):
+        return 0          # the emulator always reduces in a fixed order; the slab workspace is a property of the GPU kernels
+
     # ---- BatchNorm fold (eval)
     def _e_bn_fold(self, gamma, beta, rmean, rvar, eps, scale, bias, c, s):
         eps = eps.value if hasattr(eps, "value") else eps
@@ -126,6 +129,17 @@ class EmulatedLib:
                 for ch in range(c):
                     cols[..., (r * kw + q) * c + ch] = xp[:, ch, r:r + h, q:q + w]
         _t(dst, (n, h, w, kpad), torch.bfloat16).copy_(cols.to(torch.bfloat16))
+        return 0
+
+    # ---- 64 -> 1 heads: shifted sum of the per-tap 1x1 results
+    def _e_head_gather(self, z, z_is_half, zc, n, h, w, k, pad, tanh_out, out, s):
+        zt = _t(z, (n, h, w, zc), torch.float16 if z_is_half else torch.bfloat16).float()
+        zp = F.pad(zt.permute(0, 3, 1, 2), (pad, k - 1 - pad, pad, k - 1 - pad))      # zero rows/cols = skipped taps
+        acc = torch.zeros((n, h, w), dtype=torch.float32)
+        for r in range(k):
+            for q in range(k):
+                acc += zp[:, r * k + q, r:r + h, q:q + w]
+        _t(out, (n, h, w), torch.float32).copy_(torch.tanh(acc) if tanh_out else acc)
         return 0
 
     # ---- implicit-GEMM convolution (semantics of the gdn_conv_desc comment)

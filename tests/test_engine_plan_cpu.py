@@ -46,6 +46,7 @@ def test_eval_forward_plan_matches_oracle(name, cin):
             got = _nchw(eng.value(nm)).reshape(r.shape)
             assert relerr(got, r) <= 1e-2, (nm, relerr(got, r))
         assert emu.calls["gdn_conv2d"] == len(eng.units)
+        assert emu.calls["gdn_head_gather"] == 1          # the 64 -> 1 head runs as taps-as-N 1x1 conv + shifted sum
 
 
 def _l2rel(a, b):

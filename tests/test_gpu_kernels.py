@@ -142,6 +142,24 @@ CONV_CASES = [
     dict(N=20, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24), stats=True, f32ref=True),
     dict(N=20, H=128, W=416, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24), stats=True, f32ref=True),
     dict(N=20, H=128, W=416, cin=64, cout=64, k=1, algo=1, cin2=64, stats=True, f32ref=True),
+    # second epilogue warp group (algo bit 28: warps 8-11 take the odd 32-column groups): every channel-tile width, with
+    # and without pairs, every epilogue operator, both staging modes, and the short-reduction launches it is meant for
+    dict(N=3, H=16, W=40, cin=128, cout=64, k=1, algo=1 | (1 << 24) | (1 << 28), cin2=128, stats=True),
+    dict(N=2, H=16, W=40, cin=128, cout=128, k=1, algo=1 | (1 << 28), cin2=128, stats=True),
+    dict(N=5, H=8, W=26, cin=512, cout=512, k=3, algo=1 | (1 << 24) | (1 << 28), relu=True, bias=True, resid=True, stats=True),
+    dict(N=3, H=16, W=40, cin=256, cout=512, k=4, stride=2, reflect=True, algo=1 | (1 << 24) | (1 << 28), pad=1, stats=True),
+    dict(N=2, H=32, W=64, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 28)),
+    dict(N=3, H=16, W=40, cin=64, cout=64, k=3, algo=2 | (1 << 8) | (1 << 24) | (1 << 28), relu=True, bias=True, resid=True),
+    dict(N=2, H=32, W=64, cin=64, cout=64, k=9, algo=2 | (4 << 8) | (1 << 24) | (1 << 28), stats=True),
+    dict(N=1, H=48, W=72, cin=64, cout=64, k=9, algo=2 | (2 << 8) | (1 << 28), reflect_out=4, relu=True),
+    dict(N=3, H=16, W=52, cin=512, cout=512, k=3, algo=2 | (2 << 8) | (2 << 16) | (1 << 24) | (1 << 28), stats=True),
+    dict(N=20, H=128, W=416, cin=64, cout=64, k=1, algo=1 | (1 << 24) | (1 << 28), cin2=64, stats=True, f32ref=True),
+    # wide pixel tiles of the 1x1 launches (32 / 64 / 128 pixels per row instead of 8), ragged rows and image counts
+    dict(N=3, H=10, W=64, cin=64, cout=128, k=1, algo=1, relu=True, bias=True, resid=True),
+    dict(N=2, H=5, W=128, cin=128, cout=64, k=1, algo=1 | (1 << 24), stats=True),
+    dict(N=5, H=3, W=96, cin=64, cout=64, k=1, algo=1 | (1 << 28), cin2=64, stats=True),
+    dict(N=3, H=2, W=256, cin=64, cout=256, k=1, algo=1 | (1 << 24) | (1 << 28), stats=True),
+    dict(N=20, H=128, W=416, cin=64, cout=128, k=7, stride=2, reflect=True, algo=1 | (1 << 24) | (1 << 28), stats=True, f32ref=True),
 ]
 
 

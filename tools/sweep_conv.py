@@ -15,6 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 L = _lib.lib()
 PAIR = 1 << 24
 SPLIT = lambda s: s << 25
+EW8 = 1 << 28
 
 
 def bench(d, reps=3):
@@ -73,14 +74,16 @@ def make(cin, cout, k, stride, h, w, kind, cin1=0, pad=None):
 
 
 def name(a):
-    return "%s J%d bn%s%s%s" % ({1: "tap ", 2: "halo"}[a & 0xff], (a >> 8) & 0xff, ((a >> 16) & 0xff) * 64 or "max",
-                                " pair" if a & PAIR else "", " splitK%d" % ((a >> 25) & 7) if (a >> 25) & 7 else "")
+    return "%s J%d bn%s%s%s%s" % ({1: "tap ", 2: "halo"}[a & 0xff], (a >> 8) & 0xff, ((a >> 16) & 0xff) * 64 or "max",
+                                  " pair" if a & PAIR else "", " splitK%d" % ((a >> 25) & 7) if (a >> 25) & 7 else "",
+                                  " ew8" if a & EW8 else "")
 
 
 ALGOS = []
 for bn in (0, 1, 2, 4):
     for pair in (0, PAIR):
         ALGOS += [1 | (bn << 16) | pair] + [2 | (j << 8) | (bn << 16) | pair for j in (1, 2, 4)]
+ALGOS += [a | EW8 for a in ALGOS]
 
 SHAPES = [("512->512 k3 8x26 train", (512, 512, 3, 1, 8, 26, "train")),
           ("512->512 k3 8x26 eval", (512, 512, 3, 1, 8, 26, "eval")),
@@ -96,17 +99,22 @@ SHAPES = [("512->512 k3 8x26 train", (512, 512, 3, 1, 8, 26, "train")),
           ("512->512 k4 s2 16x52 eval", (512, 512, 4, 2, 16, 52, "eval", 0, 1)),
           ("256->256 k5 32x104 train", (256, 256, 5, 1, 32, 104, "train"))]
 
-for title, args in SHAPES:
-    d, flops, keep = make(*args)
-    rows = []
-    for a in ALGOS + ([x | SPLIT(s) for x in ALGOS for s in (2, 4)] if d.workspace else []):
-        d.algo = a
-        ms = bench(d)
-        if ms is not None:
-            rows.append((ms, a))
-    rows.sort()
-    print("== %s  (%.1f GFLOP)" % (title, flops / 1e9))
-    for ms, a in rows[:10]:
-        print("   %-28s %8.4f ms  %7.0f TFLOP/s" % (name(a), ms, flops / ms / 1e9))
-    sys.stdout.flush()
-    del keep
+def main():
+    for title, args in SHAPES:
+        d, flops, keep = make(*args)
+        rows = []
+        for a in ALGOS + ([x | SPLIT(s) for x in ALGOS for s in (2, 4)] if d.workspace else []):
+            d.algo = a
+            ms = bench(d)
+            if ms is not None:
+                rows.append((ms, a))
+        rows.sort()
+        print("== %s  (%.1f GFLOP)" % (title, flops / 1e9))
+        for ms, a in rows[:10]:
+            print("   %-28s %8.4f ms  %7.0f TFLOP/s" % (name(a), ms, flops / ms / 1e9))
+        sys.stdout.flush()
+        del keep
+
+
+if __name__ == "__main__":
+    main()
