@@ -1351,8 +1351,9 @@ def autotune_conv(L, d, reps=3, what="conv"):
     cands = _ALGOS + (_ALGOS_NARROW if small else ()) + split
     # launches with a short reduction are bound by their epilogue (one warp per scheduler: ~2 900 cycles per 32-column group
     # against K = Cin*kh*kw cycles of MMAs): let the variants with eight epilogue warps compete there
-    kred = (d.src0.c + (d.src1.c if d.src1.ptr else 0)) * d.kh * d.kw
-    if kred <= 4096 and d.cout_pad >= 64 and os.environ.get("GDN_EW8", "1") != "0":
+    # (measured, profiles/r02m_sweep_conv.log: 128->64 k1 172 -> 144 us, 64->128 k4 s2 166 -> 132 us, 512-channel k3 on
+    # 16x52 67.6 -> 64.6 us, and still 151.8 -> 149.0 us on 256 -> 256 k5 with K = 6400 -- so every launch may try them)
+    if d.cout_pad >= 64 and os.environ.get("GDN_EW8", "1") != "0":
         cands = cands + tuple(a | _EW8 for a in cands)
     for algo in cands:
         if (algo & _PAIR) and not pairs_ok:

@@ -334,8 +334,10 @@ class _StepBase:
 
     def _optim_step(self):
         self.opt.grad_scale = 1.0 / self.world     # SUM all-reduce -> average, folded into the Adam kernel
-        if self.use_graph:
-            self.opt.enable_device_step()
+        # learning rate and step count always live in device memory (what a captured graph needs), also when the step runs
+        # eagerly: both launch modes then evaluate the bias corrections with the same arithmetic, and in deterministic mode
+        # a CUDA-graph run is bit-identical to an eager one (tools/check_deterministic.py)
+        self.opt.enable_device_step()
         self.opt.step()
         self.eng._wversion = None                    # parameters changed through raw pointers: re-pack next forward
         self.model.__dict__["_gdn_epoch"] = self.model.__dict__.get("_gdn_epoch", 0) + 1   # ... in every other engine too

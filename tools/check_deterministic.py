@@ -1,7 +1,6 @@
 """GDN_DETERMINISTIC=1: are two runs of the same training steps bit-identical?  (single GPU)
-Runs K fused RtoD steps twice in this process (fresh models, fresh engines, fresh autotune -- the staging variants may
-differ between the runs: all of them accumulate the convolutions in the same order) and once more as a CUDA graph, and
-compares gradients and parameters bit for bit (the training state) and the reported loss values to 1e-9 relative: the
+Runs K fused RtoD steps twice eagerly and twice as a CUDA graph in this process (fresh models and engines every time) and
+compares them all gradients and parameters bit for bit (the training state) and the reported loss values to 1e-9 relative: the
 loss SUMS are fp64 atomics over per-CTA fp64 partials -- they only feed the value that is reported, never a gradient -- so
 their last bit may depend on the order.  Prints DET-OK / DET-FAIL.
     GDN_DETERMINISTIC=1 python tools/check_deterministic.py [steps] [batch]"""
@@ -34,17 +33,22 @@ def run(graph):
     return st.flat_params.clone(), torch.stack([l.reshape(()) for l in losses]), grads
 
 
-ref = run(False)
-ok = True
-for name, graph in (("eager (repeat)", False), ("CUDA graph", True)):
-    p, l, g = run(graph)
-    same_l = bool(((l.double() - ref[1].double()).abs() <= 1e-9 * ref[1].double().abs()).all())
-    first_bad = next((i for i, (a, b) in enumerate(zip(g, ref[2])) if not torch.equal(a, b)), None)
-    same_p = torch.equal(p, ref[0])
-    dp = (p - ref[0]).abs().max().item()
-    print("%-16s losses equal to 1e-9 %s (bitwise %s) | gradients identical %s | parameters identical %s (max |dp| %.3g)"
-          % (name, same_l, torch.equal(l, ref[1]), "yes" if first_bad is None else "first differ at step %d" % first_bad, same_p, dp))
-    ok = ok and same_l and same_p and first_bad is None
-print("losses:", ["%.7f" % v for v in ref[1].tolist()])
+def compare(name, a, b):
+    p, l, g = a
+    same_l = bool(((l.double() - b[1].double()).abs() <= 1e-9 * b[1].double().abs()).all())
+    first_bad = next((i for i, (x, y) in enumerate(zip(g, b[2])) if not torch.equal(x, y)), None)
+    same_p = torch.equal(p, b[0])
+    print("%-28s losses equal to 1e-9 %s (bitwise %s) | gradients identical %s | parameters identical %s (max |dp| %.3g)"
+          % (name, same_l, torch.equal(l, b[1]), "yes" if first_bad is None else "first differ at step %d" % first_bad, same_p,
+             (p - b[0]).abs().max().item()))
+    return same_l and same_p and first_bad is None
+
+
+e1, e2 = run(False), run(False)
+g1, g2 = run(True), run(True)
+ok = compare("eager vs eager", e2, e1)
+ok = compare("CUDA graph vs CUDA graph", g2, g1) and ok
+ok = compare("CUDA graph vs eager", g1, e1) and ok
+print("losses:", ["%.7f" % v for v in e1[1].tolist()])
 print(("DET-OK" if ok else "DET-FAIL") + " steps=%d batch=%d deterministic=%s" % (STEPS, B, det))
 sys.exit(0 if (ok or not det) else 1)
