@@ -29,6 +29,10 @@ class ConvDesc(C.Structure):
         ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p), ("out16_is_half", C.c_int32),
         ("bwd_raw", C.c_void_p), ("bwd_coef", C.c_void_p), ("bwd_relu", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("fin_counter", C.c_void_p), ("fin_gamma", C.c_void_p), ("fin_beta", C.c_void_p), ("fin_running_mean", C.c_void_p),
+        ("fin_running_var", C.c_void_p), ("fin_scale", C.c_void_p), ("fin_shift", C.c_void_p), ("fin_mean", C.c_void_p),
+        ("fin_rstd", C.c_void_p), ("fin_coef4", C.c_void_p), ("fin_count", C.c_double), ("fin_eps", C.c_float),
+        ("fin_momentum", C.c_float),
     ]
 
 

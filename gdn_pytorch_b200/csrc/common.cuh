@@ -36,6 +36,29 @@ int device_sm_count();
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
+// BatchNorm finalisation of ONE channel from its batch sums -- shared by bn_finalize_kernel (elementwise.cu) and by the
+// last CTA of a convolution (conv_igemm.cu, gdn_conv_desc.fin_*).  Every operation is an explicit round-to-nearest
+// intrinsic, so the compiler cannot contract multiply-adds differently in the two kernels: both produce the same bits.
+#ifdef __CUDACC__
+struct BnFinOut {
+  float scale, shift, mean, rstd, unbiased_var;
+};
+__device__ __forceinline__ BnFinOut bn_finalize_channel(double sum, double sq, double count, float gamma, float beta, float eps) {
+  const double m = __ddiv_rn(sum, count);
+  double var = __dsub_rn(__ddiv_rn(sq, count), __dmul_rn(m, m));
+  if (var < 0) var = 0;
+  BnFinOut o;
+  o.rstd = (float)__ddiv_rn(1.0, sqrt(__dadd_rn(var, (double)eps)));
+  o.mean = (float)m;
+  o.scale = __fmul_rn(gamma, o.rstd);
+  o.shift = __fsub_rn(beta, __fmul_rn(__fmul_rn(o.mean, gamma), o.rstd));
+  o.unbiased_var = (float)(count > 1 ? __ddiv_rn(__dmul_rn(var, count), __dsub_rn(count, 1.0)) : var);
+  return o;
+}
+__device__ __forceinline__ float bn_running_update(float running, float momentum, float value) {
+  return __fadd_rn(__fmul_rn(__fsub_rn(1.f, momentum), running), __fmul_rn(momentum, value));
+}
+#endif
 bool pdl_enabled();
 // GDN_DETERMINISTIC=1: every fp32 reduction runs in a fixed order (see det_enabled() in common.cu)
 bool det_enabled();

@@ -81,6 +81,19 @@ struct ConvK {
   float* ws;
   size_t ws_slab;
   int det;                   // GDN_DETERMINISTIC: fixed-order accumulation of the per-CTA statistics
+  // fused BatchNorm finalisation by the last CTA (see gdn_conv_desc.fin_counter)
+  unsigned int* fin_counter;
+  const float* fin_gamma;
+  const float* fin_beta;
+  float* fin_rmean;
+  float* fin_rvar;
+  float* fin_scale;
+  float* fin_shift;
+  float* fin_mean;
+  float* fin_rstd;
+  float4* fin_coef4;
+  double fin_count;
+  float fin_eps, fin_momentum;
 };
 
 struct Ring {
@@ -148,6 +161,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __shared__ uint64_t a_full[kMaxA], a_empty[kMaxA], b_full[kMaxB], b_empty[kMaxB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_stat[2][BN >= 32 ? BN : 32];
+  __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool halo = (p.mode == GDN_CONV_HALO);
@@ -605,6 +619,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
+    if (p.fin_counter) {
+      // BatchNorm finalisation by the LAST CTA whose statistics have landed (every CTA of the grid owns >= 1 tile and has
+      // flushed above): the same expressions as bn_finalize_kernel (elementwise.cu), on the finished fp64 sums
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      if (et == 0) s_last = (atomicAdd(p.fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      if (s_last) {
+        __threadfence();
+        for (int c = et; c < p.cout; c += ET) {
+          const double sum = atomicAdd(p.stat_sum + c, 0.0), sq = atomicAdd(p.stat_sq + c, 0.0);   // coherent reads
+          const BnFinOut o = bn_finalize_channel(sum, sq, p.fin_count, p.fin_gamma[c], p.fin_beta[c], p.fin_eps);
+          p.fin_scale[c] = o.scale;
+          p.fin_shift[c] = o.shift;
+          p.fin_mean[c] = o.mean;
+          p.fin_rstd[c] = o.rstd;
+          if (p.fin_coef4) p.fin_coef4[c] = make_float4(o.scale, o.shift, o.mean, o.rstd);
+          if (p.fin_rmean) {
+            p.fin_rmean[c] = bn_running_update(p.fin_rmean[c], p.fin_momentum, o.mean);
+            p.fin_rvar[c] = bn_running_update(p.fin_rvar[c], p.fin_momentum, o.unbiased_var);
+          }
+        }
+        if (et == 0) *p.fin_counter = 0u;     // ready for the next launch on this stream
+      }
+    }
   }
   tc_fence_before();
   if (CG == 2) {
@@ -882,6 +921,17 @@ extern "C" __attribute__((visibility("default"))) int gdn_conv2d(const gdn_conv_
   }
   k.ksplit = ksplit;
   k.det = det_enabled() ? 1 : 0;
+  if (d->fin_counter) {
+    if (ksplit > 1 || d->bwd_raw || !d->stat_sum || !d->stat_sqsum || !d->fin_gamma || !d->fin_beta || !d->fin_scale ||
+        !d->fin_shift || !d->fin_mean || !d->fin_rstd || !(d->fin_count > 0) || (d->fin_running_mean && !d->fin_running_var))
+      return fail(GDN_INVALID_DESC, "gdn_conv2d: fused BatchNorm finalisation needs the forward statistics, all its outputs, no split-K");
+    k.fin_counter = d->fin_counter;
+    k.fin_gamma = d->fin_gamma; k.fin_beta = d->fin_beta;
+    k.fin_rmean = d->fin_running_mean; k.fin_rvar = d->fin_running_var;
+    k.fin_scale = d->fin_scale; k.fin_shift = d->fin_shift; k.fin_mean = d->fin_mean; k.fin_rstd = d->fin_rstd;
+    k.fin_coef4 = reinterpret_cast<float4*>(d->fin_coef4);
+    k.fin_count = d->fin_count; k.fin_eps = d->fin_eps; k.fin_momentum = d->fin_momentum;
+  }
   k.ws = reinterpret_cast<float*>(d->workspace);
   k.ws_slab = (size_t)d->src0.n * d->out_h * d->out_w * d->cout;
   const int j_req = (d->algo >> 8) & 0xff;  // HALO: sub-tiles per tile requested by the caller's autotuner (0 = heuristic)

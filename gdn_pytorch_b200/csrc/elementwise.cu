@@ -199,22 +199,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double m = sum[c] / count;
-  double var = sq[c] / count - m * m;
-  if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float g = gamma[c], b = beta[c];
-  scale[c] = g * rstd;
-  shift[c] = b - (float)m * g * rstd;
-  mean_out[c] = (float)m;
-  rstd_out[c] = rstd;
+  const BnFinOut o = bn_finalize_channel(sum[c], sq[c], count, gamma[c], beta[c], eps);
+  scale[c] = o.scale;
+  shift[c] = o.shift;
+  mean_out[c] = o.mean;
+  rstd_out[c] = o.rstd;
   // what a dgrad epilogue needs per channel for the fused BatchNorm-backward statistics: y = x*scale + shift (ReLU
   // mask), xhat = (x - mean)*rstd -- the same expressions gdn_bn_bwd_reduce evaluates
-  if (coef4) coef4[c] = make_float4(g * rstd, b - (float)m * g * rstd, (float)m, rstd);
+  if (coef4) coef4[c] = make_float4(o.scale, o.shift, o.mean, o.rstd);
   if (running_mean) {
-    const double unb = count > 1 ? var * count / (count - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    running_mean[c] = bn_running_update(running_mean[c], momentum, o.mean);
+    running_var[c] = bn_running_update(running_var[c], momentum, o.unbiased_var);
   }
 }
 

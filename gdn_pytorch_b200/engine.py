@@ -127,6 +127,7 @@ class Engine:
         # staging variants group the pixels differently, i.e. sum the BatchNorm statistics in a different fp32 order)
         if os.environ.get("GDN_AUTOTUNE", "1") != "0" and not self.det and not torch.cuda.is_current_stream_capturing():
             self.autotune()
+        self._attach_bn_finalize()
 
     # ------------------------------------------------------------------ shapes
     def _infer_shapes(self):
@@ -316,7 +317,11 @@ class Engine:
             # per-channel sum / sum-of-squares accumulators of EVERY BatchNorm of the network in one fp64 buffer,
             # cleared by one launch at the head of the forward plan (instead of one tiny fill per layer on the
             # critical chain)
-            self.stat_all = torch.zeros(sum(2 * u.cout for u in self.units if u.bn is not None) + 2, dtype=torch.float64,
+            # (+ one 8-byte slot per BatchNorm layer behind the sums: the "statistics flushed" counters of the fused
+            # finalisation, cleared by the same launch)
+            n_stat = sum(2 * u.cout for u in self.units if u.bn is not None)
+            self._fin_slot = n_stat + 2
+            self.stat_all = torch.zeros(n_stat + 2 + sum(1 for u in self.units if u.bn is not None), dtype=torch.float64,
                                         device=dev)
             zero_stats = lambda s: self.stat_all.zero_()
             zero_stats.label = "misc"
@@ -440,7 +445,16 @@ class Engine:
                 rm, rv = P[u.bn + ".running_mean"], P[u.bn + ".running_var"]
                 cnt = float(N * ho * wo)
 
+                # BatchNorm finalisation (statistics -> scale / shift / mean / rstd, running statistics): by the LAST CTA of
+                # the convolution itself (gdn_conv_desc.fin_*), attached after the autotuner has run (its timing launches
+                # must not touch the running statistics); the separate launch remains for GDN_FUSE_BNFIN=0
+                cu.fin = (self.stat_all[self._fin_slot:self._fin_slot + 1], g_, b_, rm, rv, cnt)
+                self._fin_slot += 1
+                cu.fin_fused = False
+
                 def finalize(s, cu=cu, g_=g_, b_=b_, rm=rm, rv=rv, cnt=cnt, c=u.cout):
+                    if cu.fin_fused:
+                        return
                     rc = L.gdn_bn_finalize(C.c_void_p(cu.stat[0].data_ptr()), C.c_void_p(cu.stat[1].data_ptr()),
                                            C.c_double(cnt), C.c_void_p(g_.data_ptr()), C.c_void_p(b_.data_ptr()),
                                            C.c_float(BN_EPS), C.c_float(BN_MOMENTUM), C.c_void_p(rm.data_ptr()),
@@ -828,6 +842,9 @@ class Engine:
             wd.off_y, wd.off_x = fd.off_y, fd.off_x
             wd.out_h, wd.out_w, wd.cout_pad = ho, wo, u.cout
             used = self._det_slabs(wd)
+            # (the accumulating kernel needs a clean scratch.  Letting the unpack write zeros back to what it read instead
+            # of these 46 fills was measured and rejected: unpack 0.77 -> 1.34 ms per step against 0.19 ms of fills,
+            # profiles/r02p_profile_ops.log; the slab mode stores and needs neither)
             zero_dw = lambda s, dw=dw: dw.zero_()
             zero_dw.label = "misc"
             side_ops = ([] if used is not None else [zero_dw]) + [self._call(L.gdn_conv2d_wgrad, wd, "wgrad " + u.conv)]
@@ -1204,6 +1221,25 @@ class Engine:
         self.grad_ready_op[u.conv + ".weight"] = len(self.bwd) - 1
         self.launches_bwd += 5
         cu.keep = [wdg]
+
+    def _attach_bn_finalize(self):
+        """fuse every BatchNorm finalisation into the tail of its convolution (last CTA), see include/gdn_b200.h"""
+        if not self.train or os.environ.get("GDN_FUSE_BNFIN", "1") == "0":
+            return
+        for cu in self.cu.values():
+            fin = getattr(cu, "fin", None)
+            d = getattr(cu, "conv_desc", None)
+            if fin is None or d is None or ((d.algo >> 25) & 7) >= 2:
+                continue
+            slot, g_, b_, rm, rv, cnt = fin
+            d.fin_counter = slot.data_ptr()
+            d.fin_gamma, d.fin_beta = g_.data_ptr(), b_.data_ptr()
+            d.fin_running_mean, d.fin_running_var = rm.data_ptr(), rv.data_ptr()
+            d.fin_scale, d.fin_shift = cu.scale.data_ptr(), cu.shift.data_ptr()
+            d.fin_mean, d.fin_rstd, d.fin_coef4 = cu.mean.data_ptr(), cu.rstd.data_ptr(), cu.coef4.data_ptr()
+            d.fin_count, d.fin_eps, d.fin_momentum = cnt, BN_EPS, BN_MOMENTUM
+            cu.fin_fused = True
+            self.launches_fwd -= 1
 
     _DET_MAX_SLABS = 32
 

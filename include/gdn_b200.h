@@ -102,6 +102,23 @@ typedef struct {
    * epilogue above.  Plain destinations only (no strides, border, reflection, tanh; cout a power of two). */
   void* workspace;
   size_t workspace_bytes;
+  /* Fused BatchNorm finalisation (training forward, optional): with `fin_counter` set (a device uint32 that is 0 before
+   * the launch; the launch leaves it 0), the LAST CTA to flush its statistics turns stat_sum / stat_sqsum into what
+   * gdn_bn_finalize would compute from them -- same expressions, same results -- so the separate finalise launch between
+   * the convolution and the BatchNorm-apply pass disappears: scale = gamma*rstd, shift = beta - mean*scale, mean, rstd,
+   * coef4 (optional), running statistics (momentum, unbiased variance; optional).  Not with split-K or bwd_raw. */
+  uint32_t* fin_counter;
+  const float* fin_gamma;
+  const float* fin_beta;
+  float* fin_running_mean;   /* may be NULL */
+  float* fin_running_var;
+  float* fin_scale;
+  float* fin_shift;
+  float* fin_mean;
+  float* fin_rstd;
+  float* fin_coef4;          /* may be NULL */
+  double fin_count;
+  float fin_eps, fin_momentum;
 } gdn_conv_desc;
 
 int gdn_conv2d(const gdn_conv_desc* d, gdn_stream stream);

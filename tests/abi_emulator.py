@@ -169,6 +169,11 @@ class EmulatedLib:
         if d.stat_sum and not d.bwd_raw:
             _t(d.stat_sum, (d.cout,), torch.float64).add_(acc.double().sum((0, 1, 2)))
             _t(d.stat_sqsum, (d.cout,), torch.float64).add_((acc.double() ** 2).sum((0, 1, 2)))
+            if d.fin_counter:      # fused BatchNorm finalisation: what the last CTA does with the finished sums
+                assert int(_t(d.fin_counter, (1,), torch.int32)[0]) == 0, "fin_counter must be 0 before the launch"
+                self._e_bn_finalize(d.stat_sum, d.stat_sqsum, d.fin_count, d.fin_gamma, d.fin_beta, d.fin_eps, d.fin_momentum,
+                                    d.fin_running_mean, d.fin_running_var, d.fin_scale, d.fin_shift, d.fin_mean, d.fin_rstd,
+                                    d.fin_coef4, d.cout, s)
         v = acc
         if d.bias:
             v = v + _t(d.bias, (d.cout,), torch.float32)

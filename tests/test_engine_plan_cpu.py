@@ -111,10 +111,12 @@ def test_training_plan_forward_backward_matches_autograd(gname):
     x = synth.synth_rgb(B, H, W, 1) if g.cin == 3 else synth.synth_depth(B, H, W, 1)
     R = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(5)) - 0.5
     names = [u.out for u in g.units]
-    with emulated_abi():
+    with emulated_abi() as emu:
         eng = Engine(g, sd, B, H, W, train=True, backward=True, want=names, device=torch.device("cpu"))
         with torch.no_grad():
             engine_forward(eng, x)
+            # BatchNorm finalisation rides on the tail of the convolutions (gdn_conv_desc.fin_*): no separate launches
+            assert "gdn_bn_finalize" not in emu.calls and all(cu.fin_fused for cu in eng.cu.values() if hasattr(cu, "fin"))
             masks = {u.out: (eng.value_nchw(u.out) > 0) for u in g.units if u.relu and not u.resid}
             out = eng.depth()
             eng.flat_grad.zero_()

@@ -276,6 +276,15 @@ def test_pack_weights_and_unpack_wgrad(cout, cin, k, transposed):
     else:
         inc = dw.view(k, k, cin, cout).permute(3, 2, 0, 1)
     assert torch.allclose(grad, before + inc, rtol=0, atol=1e-6)
+    # slabs (deterministic split-K): partial gradients lying slab_elems apart are summed in index order
+    parts = torch.randn((3,) + tuple(dw.shape), generator=g).to(dev)
+    grad3 = torch.zeros_like(grad)
+    _lib.check(L.gdn_unpack_wgrad_slabs(C.byref(pd), C.c_void_p(parts.data_ptr()), 3, C.c_int64(dw.numel()),
+                                        C.c_void_p(grad3.data_ptr()), 0, _lib.stream_ptr()), "unpack slabs")
+    torch.cuda.synchronize()
+    tot = ((parts[0] + parts[1]) + parts[2])
+    inc3 = tot.view(k, k, cin, cout).permute(2, 3, 0, 1).flip(2, 3) if transposed else tot.view(k, k, cin, cout).permute(3, 2, 0, 1)
+    assert torch.equal(grad3, inc3.contiguous())
 
 
 def test_pack_weights_table_matches_per_tensor_packs():

@@ -94,6 +94,48 @@ def _conv_case(N, H, W, cin, cout, k, stride=1, reflect=False, algo=0, relu=Fals
     if stats:
         assert torch.allclose(ssum[0], raw.double().sum((0, 2, 3)), rtol=1e-4, atol=1e-3 * scale * (10 if f32ref else 1))
         assert torch.allclose(ssum[1], (raw.double() ** 2).sum((0, 2, 3)), rtol=1e-4)
+    if stats and not ((algo >> 25) & 7):
+        _fused_finalize_case(d, cout, N * OH * OW, seed)
+
+
+def _fused_finalize_case(d, cout, count, seed):
+    """gdn_conv_desc.fin_*: the last CTA of the convolution finalises BatchNorm from the sums it has just completed --
+    bit-identical to gdn_bn_finalize applied to the same sums; the flush counter returns to 0 (two launches in a row)"""
+    from gdn_pytorch_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(seed + 77)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    beta = (torch.rand(cout, generator=g) - 0.5).to(dev)
+    rm0, rv0 = (torch.rand(cout, generator=g) - 0.5).to(dev), (torch.rand(cout, generator=g) + 0.5).to(dev)
+    ssum = torch.zeros((2, cout), dtype=torch.float64, device=dev)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    d.stat_sum, d.stat_sqsum = ssum[0].data_ptr(), ssum[1].data_ptr()
+    for rep in range(2):
+        ssum.zero_()
+        rm, rv = rm0.clone(), rv0.clone()
+        outs = [torch.full((cout,), float("nan"), device=dev) for _ in range(4)]
+        coef = torch.full((cout, 4), float("nan"), device=dev)
+        d.fin_counter = counter.data_ptr()
+        d.fin_gamma, d.fin_beta = gamma.data_ptr(), beta.data_ptr()
+        d.fin_running_mean, d.fin_running_var = rm.data_ptr(), rv.data_ptr()
+        d.fin_scale, d.fin_shift, d.fin_mean, d.fin_rstd = (t.data_ptr() for t in outs)
+        d.fin_coef4 = coef.data_ptr()
+        d.fin_count, d.fin_eps, d.fin_momentum = float(count), 1e-5, 0.1
+        _lib.check(L.gdn_conv2d(C.byref(d), _lib.stream_ptr()), "conv + fused finalize")
+        torch.cuda.synchronize()
+        assert int(counter[0]) == 0
+        rm2, rv2 = rm0.clone(), rv0.clone()
+        ref = [torch.empty(cout, device=dev) for _ in range(4)]
+        coef2 = torch.empty((cout, 4), device=dev)
+        _lib.check(L.gdn_bn_finalize(C.c_void_p(ssum[0].data_ptr()), C.c_void_p(ssum[1].data_ptr()), C.c_double(float(count)),
+                                     C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), C.c_float(1e-5), C.c_float(0.1),
+                                     C.c_void_p(rm2.data_ptr()), C.c_void_p(rv2.data_ptr()), C.c_void_p(ref[0].data_ptr()),
+                                     C.c_void_p(ref[1].data_ptr()), C.c_void_p(ref[2].data_ptr()), C.c_void_p(ref[3].data_ptr()),
+                                     C.c_void_p(coef2.data_ptr()), cout, _lib.stream_ptr()), "bn_finalize")
+        torch.cuda.synchronize()
+        for a, b in zip(outs + [coef, rm, rv], ref + [coef2, rm2, rv2]):
+            assert torch.equal(a, b)
+    d.fin_counter = None
 
 
 CONV_CASES = [
