@@ -204,6 +204,147 @@ __global__ void loss_kernel(const LossK k) {
   }
 }
 
+// RtoD loss, vectorised (mode 0, W % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive pixels of a row.  Everything
+// it needs -- the output row and the rows above / below, ground truth, sparse mask, three rows of the three image planes --
+// is 14 independent float4 loads + 8 scalar edge loads issued back to back (the scalar kernel above issues ~40 dependent-
+// address scalar loads per pixel and spends its time in load latency: 40 us for 30 MB, profiles/r02e_ncu_metrics.summary.txt).
+// The per-pixel expressions are the ones of loss_kernel, operation for operation (gradients agree to fp32 rounding); the
+// three loss SUMS are accumulated in fp32 over a thread's four pixels, then in fp64.
+__global__ void __launch_bounds__(256) loss_rows_kernel(const LossK k, const int lg_tpr) {
+  pdl_trigger();
+  pdl_wait();
+  const int W = k.W, H = k.H;
+  const long long HW = (long long)H * W;
+  const float c = 0.2f * (*k.maxabs);
+  const int tpr = 1 << lg_tpr;                       // threads per row
+  const int rpi = (int)blockDim.x >> lg_tpr;         // rows per CTA iteration
+  const int tx = threadIdx.x & (tpr - 1), tr = threadIdx.x >> lg_tpr;
+  const long long rows = (long long)k.N * H;
+  double acc[3] = {0.0, 0.0, 0.0};
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * rpi + tr; row < rows; row += (long long)gridDim.x * rpi) {
+    const long long n = row / H;
+    const int y = (int)(row - n * H);
+    const float* o = k.out + n * HW + (long long)y * W;
+    const float* g = k.gt + n * HW + (long long)y * W;
+    const float* sp = k.sparse ? k.sparse + n * k.sparse_stride + (long long)y * W : nullptr;
+    const float* I = k.rgb + n * 3 * HW + (long long)y * W;
+    const bool up = y >= 1, dn = y < H - 1;
+    for (int x0 = 4 * tx; x0 < W; x0 += 4 * tpr) {
+      // ---- loads (all independent)
+      const float4 o1 = *reinterpret_cast<const float4*>(o + x0);
+      const float4 o0 = up ? *reinterpret_cast<const float4*>(o - W + x0) : z4;
+      const float4 o2 = dn ? *reinterpret_cast<const float4*>(o + W + x0) : z4;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + x0);
+      const float4 s4 = sp ? *reinterpret_cast<const float4*>(sp + x0) : z4;
+      float4 i0[3], i1[3], i2[3];
+      float il[3], ir[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        const float* Ic = I + ch * HW;
+        i1[ch] = *reinterpret_cast<const float4*>(Ic + x0);
+        i0[ch] = up ? *reinterpret_cast<const float4*>(Ic - W + x0) : z4;
+        i2[ch] = dn ? *reinterpret_cast<const float4*>(Ic + W + x0) : z4;
+        il[ch] = x0 >= 1 ? Ic[x0 - 1] : 0.f;
+        ir[ch] = x0 + 4 < W ? Ic[x0 + 4] : 0.f;
+      }
+      const float ol = x0 >= 1 ? o[x0 - 1] : 0.f, orr = x0 + 4 < W ? o[x0 + 4] : 0.f;
+      // ---- edge weights: wx[j] = weight of the forward difference starting at x0 - 1 + j (j = 0..4), wy1 at (y, x), wy0 at (y-1, x)
+      const float ov[6] = {ol, o1.x, o1.y, o1.z, o1.w, orr};
+      float Iv[3][6];
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        Iv[ch][0] = il[ch]; Iv[ch][1] = i1[ch].x; Iv[ch][2] = i1[ch].y; Iv[ch][3] = i1[ch].z; Iv[ch][4] = i1[ch].w; Iv[ch][5] = ir[ch];
+      }
+      float wx[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        float sd = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) sd += fabsf(Iv[ch][j] - Iv[ch][j + 1]);
+        wx[j] = expf(-sd / 3.f);
+      }
+      const float* p0[3] = {&i0[0].x, &i0[1].x, &i0[2].x};
+      const float* p2[3] = {&i2[0].x, &i2[1].x, &i2[2].x};
+      const float* po0 = &o0.x;
+      const float* po2 = &o2.x;
+      const float* pg = &g4.x;
+      const float* ps = &s4.x;
+      float part0 = 0.f, part1 = 0.f, part2 = 0.f;
+      float gr[4], dp[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int x = x0 + e;
+        const float ovx = ov[e + 1];
+        const float d = ovx - pg[e];
+        const float a = fabsf(d);
+        float wgt = 1.f;
+        if (sp) {
+          const bool crop = (y >= k.cy1 && y < k.cy2 && x >= k.cx1 && x < k.cx2);
+          if (!crop) wgt = 0.1f;
+          else if (!(ps[e] > -1.f)) wgt = 0.3f;
+        }
+        float val, dv;
+        if (a > c) {
+          val = (d * d + c * c) / (2.f * c);
+          dv = d / c;
+        } else {
+          val = a;
+          dv = sgn(d);
+        }
+        part0 += val * wgt;
+        part2 += d * d;
+        float grad = 3.f * k.inv_count * wgt * dv;
+        float sm = 0.f, gs = 0.f;
+        if (x < W - 1) {
+          const float gx = ovx - ov[e + 2];
+          const float w = wx[e + 1];
+          sm += fabsf(gx) * w;
+          gs += sgn(gx) * w;
+        }
+        if (x >= 1) {
+          const float gx = ov[e] - ovx;
+          gs -= sgn(gx) * wx[e];
+        }
+        if (dn) {
+          float sd = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) sd += fabsf(Iv[ch][e + 1] - p2[ch][e]);
+          const float w = expf(-sd / 3.f);
+          const float gy = ovx - po2[e];
+          sm += fabsf(gy) * w;
+          gs += sgn(gy) * w;
+        }
+        if (up) {
+          float sd = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) sd += fabsf(p0[ch][e] - Iv[ch][e + 1]);
+          const float gy = po0[e] - ovx;
+          gs -= sgn(gy) * expf(-sd / 3.f);
+        }
+        part1 += sm;
+        grad += 0.1f * k.inv_count * gs;
+        grad *= k.grad_scale;
+        gr[e] = grad;
+        dp[e] = grad * (1.f - ovx * ovx);
+      }
+      const long long off = row * W + x0;
+      if (k.dout) *reinterpret_cast<float4*>(k.dout + off) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+      if (k.dpre) *reinterpret_cast<float4*>(k.dpre + off) = make_float4(dp[0], dp[1], dp[2], dp[3]);
+      acc[0] += (double)part0;
+      acc[1] += (double)part1;
+      acc[2] += (double)part2;
+    }
+  }
+  __shared__ double sred[32 * 3];
+  block_sum_d<3>(acc, sred);
+  if (threadIdx.x == 0) {
+    atomicAdd(k.sums + 0, acc[0]);
+    atomicAdd(k.sums + 1, acc[1]);
+    atomicAdd(k.sums + 2, acc[2]);
+  }
+}
+
 // ------------------------------------------------------------------------------- sum of squared diffs
 __global__ void sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4,
                                   double* __restrict__ out) {
@@ -615,6 +756,24 @@ GDN_API int gdn_loss(const gdn_loss_desc* d, gdn_stream stream) {
   k.inv_count = 1.0f / (float)((long long)d->n * d->h * d->w);
   k.sums = d->sums; k.dout = d->dout; k.dpre = d->dpre;
   k.grad_scale = d->grad_scale;
+  {
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = d->mode == 0 && d->w % 4 == 0 && d->w >= 8 && al16(d->out) && al16(d->gt) && al16(d->rgb) &&
+                     (!d->sparse || (al16(d->sparse) && d->sparse_stride % 4 == 0)) && (!d->dout || al16(d->dout)) &&
+                     (!d->dpre || al16(d->dpre));
+    if (vec) {
+      int lg = 1;                                  // threads per row: power of two >= w / 4, at most the CTA
+      while ((1 << lg) < d->w / 4 && lg < 8) lg++;
+      const long long rows = (long long)d->n * d->h;
+      const int rpi = 256 >> lg;
+      long long ctas = (rows + rpi - 1) / rpi;
+      const long long cap = (long long)device_sm_count() * 4;
+      if (ctas > cap) ctas = cap;
+      GDN_CUDA_CHECK(launch_pdl(loss_rows_kernel, dim3((unsigned)ctas), dim3(256), 0, (cudaStream_t)stream, 1, k, lg));
+      GDN_LAUNCH_CHECK("loss_rows_kernel");
+      return GDN_OK;
+    }
+  }
   GDN_CUDA_CHECK(launch_pdl(loss_kernel, dim3(lm_grid((long long)d->n * d->h * d->w, 256)), dim3(256), 0, (cudaStream_t)stream, 1, k));
   GDN_LAUNCH_CHECK("loss_kernel");
   return GDN_OK;
