@@ -21,13 +21,13 @@ export GDN_GRAPH=0 GDN_PROFILE_LAST=1
 NCU="ncu --profile-from-start off --clock-control none"
 timeout 500 $NCU --metrics gpu__time_duration.sum,launch__grid_size --csv --log-file $O/${TAG}_launches.csv python tools/profile_step.py 3 > $O/${TAG}_ncu_launches.log 2>&1
 python tools/launch_summary.py $O/${TAG}_launches.csv > $O/${TAG}_launches_by_kernel.txt 2>&1; head -34 $O/${TAG}_launches_by_kernel.txt
-timeout 600 $NCU --set full --import-source on -k regex:'head_gather|bn_bwd|fold_rows|act_up_rows|up2x|act_rows|adam_kernel|unpack_tile|pack_table|im2col' -c 40 -f -o /tmp/${TAG}_elem python tools/profile_step.py 3 > $O/${TAG}_ncu_elem.log 2>&1
+timeout 600 $NCU --set full --import-source on -k regex:'head_gather|bn_bwd|fold_rows|act_up_rows|up2x|act_rows|adam_kernel|unpack_tile|pack_table|im2col' -c 220 -f -o /tmp/${TAG}_elem python tools/profile_step.py 3 > $O/${TAG}_ncu_elem.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_elem.ncu-rep > $O/${TAG}_ncu_elem.summary.txt 2>&1
 unset GDN_PROFILE_LAST
 timeout 300 $NCU --set full --import-source on -k regex:conv_igemm -c 2 -f -o $O/${TAG}_conv64k9 python tools/profile_conv.py 20 > $O/${TAG}_ncu_conv64k9.log 2>&1
 python tools/ncu_summary.py $O/${TAG}_conv64k9.ncu-rep --traffic-json $O/${TAG}_dominant_conv_traffic.json conv_igemm > $O/${TAG}_ncu_conv64k9.summary.txt 2>&1
 cat $O/${TAG}_ncu_conv64k9.summary.txt
-timeout 300 $NCU --set full --import-source on -k regex:'metrics_|loss_kernel|absdiff' -c 16 -f -o /tmp/${TAG}_metrics python tools/profile_metrics.py > $O/${TAG}_ncu_metrics.log 2>&1
+timeout 300 $NCU --set full --import-source on -k regex:'metrics_|loss_|absdiff' -c 16 -f -o /tmp/${TAG}_metrics python tools/profile_metrics.py > $O/${TAG}_ncu_metrics.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_metrics.ncu-rep > $O/${TAG}_ncu_metrics.summary.txt 2>&1
 cut -c1-260 $O/${TAG}_ncu_metrics.summary.txt
 grep -v "OMP_NUM\|\*\*\*\*\|^$" $O/${TAG}_bench.err | tail -4 | cut -c1-300; du -sh $O
