@@ -928,7 +928,8 @@ __global__ void fold_grad_kernel(const FoldK f) {
 // source row once per row; the per-item loop is loads + FMAs only (a first version that recomputed the candidates per
 // item was ALU-bound at ~1 TB/s on the x2-bilinear adjoints; same-box A/B in profiles/r02a_*).  Dynamic shared memory:
 // W * 64 bytes.
-__global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
+template <int CV>
+__global__ void __launch_bounds__(kEwThreads, 2) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char s_fold[];
@@ -940,13 +941,13 @@ __global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, c
   const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
   const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
   for (int x = threadIdx.x; x < f.W; x += kEwThreads) fold_col_entry(f, OW, x, s_pc + x * kFoldColInts, s_qw + x * 4);
-  const int items = f.W << lg_cg;
+  const int items = f.W << lg_cg;           // (x, CV-channel group) pairs of one source row
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) s_np = fold_row_entry(f, OH, row % f.H, s_prow, s_pw);
     __syncthreads();
     const int np = s_np;
-    for (int it = threadIdx.x; it < items; it += kEwThreads) fold_item(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc, s_qw);
+    for (int it = threadIdx.x; it < items; it += kEwThreads) fold_item_t<CV>(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc, s_qw);
   }
 }
 
@@ -1391,12 +1392,15 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
     return GDN_OK;
   }
   {
-    const int lg = ew_lg2(f.C / 4);
+    // 8 channels per thread when every 8-channel group is 16-byte aligned in both tensors, else 4
+    const bool v8 = f.C % 8 == 0 && f.ctot % 8 == 0 && f.c_off % 8 == 0 && ew_lg2(f.C / 8) >= 0;
+    const int lg = v8 ? ew_lg2(f.C / 8) : ew_lg2(f.C / 4);
     if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
       const int rows = f.N * f.H;
       const size_t smem = (size_t)f.W * (kFoldColInts * sizeof(int) + 4 * sizeof(float));
       if (smem <= 40 * 1024) {
-        GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
+        if (v8) GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel<8>, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
+        else GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel<4>, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
         GDN_LAUNCH_CHECK("fold_rows2_kernel");
         return GDN_OK;
       }
@@ -1510,7 +1514,11 @@ GDN_API int gdn_unpack_wgrad_slabs(const gdn_pack_desc* d, const float* dw, int 
   const long long se = (long long)slab_elems;
   PackK k;
   fill_pack(d, k);
-  if (pack_tileable(k)) {
+  // the tile kernel launches one CTA per 16 x 16 (a, b) tile for ALL taps: a 64 x 64 tensor with 81 taps would be 16 CTAs
+  // walking 20 736 elements each (90 us for 1.3 MB, profiles/r02r_ncu_elem.summary.txt) -- such tensors take the
+  // element-parallel kernel below (coalesced reads, scattered 4-byte writes that the L2 absorbs)
+  const bool enough_tiles = ((k.A + kPackTile - 1) / kPackTile) * ((k.B + kPackTile - 1) / kPackTile) >= 64;
+  if (pack_tileable(k) && enough_tiles) {
     const int T = k.kh * k.kw;
     const size_t smem = (size_t)kPackTile * kPackTile * (T + 1) * sizeof(float);
     static bool configured[64] = {false};
