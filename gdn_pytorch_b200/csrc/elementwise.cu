@@ -928,8 +928,9 @@ __global__ void fold_grad_kernel(const FoldK f) {
 // source row once per row; the per-item loop is loads + FMAs only (a first version that recomputed the candidates per
 // item was ALU-bound at ~1 TB/s on the x2-bilinear adjoints; same-box A/B in profiles/r02a_*).  Dynamic shared memory:
 // W * 64 bytes.
-template <int CV>
-__global__ void __launch_bounds__(kEwThreads, 2) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
+// (A version with 8 channels per thread and the up-to-12 candidate loads of a buffer row issued together was measured and
+// rejected: 1.21 -> 1.71 ms per step over the eight folds, profiles/r02u_profile_ops.log -- 128 registers, two CTAs per SM.)
+__global__ void __launch_bounds__(kEwThreads) fold_rows2_kernel(const FoldK f, const int lg_cg, const int rows) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char s_fold[];
@@ -941,13 +942,13 @@ __global__ void __launch_bounds__(kEwThreads, 2) fold_rows2_kernel(const FoldK f
   const int OH = (f.up || f.dilate) ? 2 * f.H : f.H, OW = (f.up || f.dilate) ? 2 * f.W : f.W;
   const int Hq = OH + 2 * f.P, Wq = OW + 2 * f.P;
   for (int x = threadIdx.x; x < f.W; x += kEwThreads) fold_col_entry(f, OW, x, s_pc + x * kFoldColInts, s_qw + x * 4);
-  const int items = f.W << lg_cg;           // (x, CV-channel group) pairs of one source row
+  const int items = f.W << lg_cg;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) s_np = fold_row_entry(f, OH, row % f.H, s_prow, s_pw);
     __syncthreads();
     const int np = s_np;
-    for (int it = threadIdx.x; it < items; it += kEwThreads) fold_item_t<CV>(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc, s_qw);
+    for (int it = threadIdx.x; it < items; it += kEwThreads) fold_item(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc, s_qw);
   }
 }
 
@@ -1392,15 +1393,12 @@ GDN_API int gdn_fold_grad(const gdn_fold_desc* d, gdn_stream stream) {
     return GDN_OK;
   }
   {
-    // 8 channels per thread when every 8-channel group is 16-byte aligned in both tensors, else 4
-    const bool v8 = f.C % 8 == 0 && f.ctot % 8 == 0 && f.c_off % 8 == 0 && ew_lg2(f.C / 8) >= 0;
-    const int lg = v8 ? ew_lg2(f.C / 8) : ew_lg2(f.C / 4);
+    const int lg = ew_lg2(f.C / 4);
     if (lg >= 0 && (long long)f.W * (f.C / 4) < (1ll << 30) && (long long)f.N * f.H < (1ll << 30)) {
       const int rows = f.N * f.H;
       const size_t smem = (size_t)f.W * (kFoldColInts * sizeof(int) + 4 * sizeof(float));
       if (smem <= 40 * 1024) {
-        if (v8) GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel<8>, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
-        else GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel<4>, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
+        GDN_CUDA_CHECK(launch_pdl(fold_rows2_kernel, dim3(ew_row_grid(rows)), dim3(kEwThreads), smem, (cudaStream_t)stream, 1, f, lg, rows));
         GDN_LAUNCH_CHECK("fold_rows2_kernel");
         return GDN_OK;
       }

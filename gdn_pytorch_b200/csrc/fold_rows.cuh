@@ -124,64 +124,39 @@ GDN_HD int fold_row_entry(const FoldK& f, int OH, int y, int* prow, float* pw) {
   return np;
 }
 
-// one (x, CV-channel group) item of source row `row`, CV = 4 or 8.  Per buffer row the (up to 12) candidate loads are
-// issued TOGETHER before anything is accumulated -- the first version of this loop loaded and accumulated candidate by
-// candidate, i.e. ran one memory latency per candidate (0.96 TB/s on the 404 MB of the largest fold,
-// profiles/r02r_ncu_elem.summary.txt) -- and then accumulated in the same (candidate, image) order as before.
-// CV = 8 halves the thread count and doubles the bytes per load (16 B of bf16, 2 x 16 B of fp32).
-template <int CV>
-GDN_HD void fold_item_t(const FoldK& f, int lg_cg, int Hq, int Wq, int row, int it, int np, const int* prow, const float* pw,
-                        const int* pcs, const float* qws) {
+// one (x, 4-channel group) item of source row `row`: same accumulation order as the first version of the kernel
+GDN_HD void fold_item(const FoldK& f, int lg_cg, int Hq, int Wq, int row, int it, int np, const int* prow, const float* pw,
+                      const int* pcs, const float* qws) {
   const int cgm = (1 << lg_cg) - 1;
-  const int x = it >> lg_cg, c0 = (it & cgm) * CV;
+  const int x = it >> lg_cg, c4 = (it & cgm) * 4;
   const int n = row / f.H;
   const size_t img = (size_t)n * Hq;
   const int* pc = pcs + (size_t)x * kFoldColInts;
   const float* qw = qws + (size_t)x * 4;
-  int col[kFoldColInts];
-  float wk[4];
-  for (int j = 0; j < kFoldColInts; j++) col[j] = pc[j];
-  for (int k = 0; k < 4; k++) wk[k] = qw[k];
-  float acc[CV];
-  for (int e = 0; e < CV; e++) acc[e] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int p = 0; p < np; p++) {
-    const size_t rowo = ((img + prow[p]) * Wq) * f.ctot + f.c_off + c0;
+    const size_t rowo = ((img + prow[p]) * Wq) * f.ctot + f.c_off + c4;
     const float wr = pw[p];
-    FoldV4 v[kFoldColInts][CV / 4];
+    for (int k = 0; k < 4; k++) {
+      const float w = wr * qw[k];
+      for (int m = 0; m < 3; m++) {
+        const int col = pc[3 * k + m];
+        if (col < 0) continue;
+        const FoldV4 v = fold_load4(f, rowo + (size_t)col * f.ctot);
 #if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < kFoldColInts; j++) {
-      if (col[j] < 0) continue;
-      for (int h = 0; h < CV / 4; h++) v[j][h] = fold_load4(f, rowo + (size_t)col[j] * f.ctot + 4 * h);
-    }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < kFoldColInts; j++) {
-      if (col[j] < 0) continue;
-      const float w = wr * wk[j / 3];
-      for (int h = 0; h < CV / 4; h++) {
-#if defined(__CUDA_ARCH__)
-        acc[4 * h + 0] = fmaf(w, v[j][h].x, acc[4 * h + 0]); acc[4 * h + 1] = fmaf(w, v[j][h].y, acc[4 * h + 1]);
-        acc[4 * h + 2] = fmaf(w, v[j][h].z, acc[4 * h + 2]); acc[4 * h + 3] = fmaf(w, v[j][h].w, acc[4 * h + 3]);
+        acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
 #else
-        acc[4 * h + 0] += w * v[j][h].x; acc[4 * h + 1] += w * v[j][h].y;
-        acc[4 * h + 2] += w * v[j][h].z; acc[4 * h + 3] += w * v[j][h].w;
+        acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
 #endif
       }
     }
   }
-  float* o = f.dact + ((size_t)row * f.W + x) * f.C + c0;
-  for (int h = 0; h < CV / 4; h++) {
-    float* oh = o + 4 * h;
-    float r0 = acc[4 * h], r1 = acc[4 * h + 1], r2 = acc[4 * h + 2], r3 = acc[4 * h + 3];
-    if (f.accumulate) {
-      const float4 u = *reinterpret_cast<const float4*>(oh);
-      r0 += u.x; r1 += u.y; r2 += u.z; r3 += u.w;
-    }
-    *reinterpret_cast<float4*>(oh) = make_float4(r0, r1, r2, r3);
+  float* o = f.dact + ((size_t)row * f.W + x) * f.C + c4;
+  if (f.accumulate) {
+    const float4 v = *reinterpret_cast<const float4*>(o);
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
   }
+  *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 }  // namespace gdn

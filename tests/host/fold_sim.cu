@@ -8,13 +8,12 @@
 using namespace gdn;
 
 extern "C" int fold_rows2_host(const float* dpad, int ctot, int c_off, int N, int H, int W, int C, int P, int reflect, int up,
-                               int dilate, float* dact, int accumulate, int nthreads, int nblocks, int cv) {
+                               int dilate, float* dact, int accumulate, int nthreads, int nblocks) {
   FoldK f{dpad, ctot, c_off, N, H, W, C, P, reflect, up, dilate, dact, accumulate, 0};
-  if (cv != 4 && cv != 8) return -2;      // channels per thread: the two instantiations of fold_rows2_kernel
   int lg_cg = -1;
   for (int l = 0; l < 16; l++)
-    if ((1 << l) == C / cv) lg_cg = l;
-  if (lg_cg < 0 || C % cv || (cv == 8 && (ctot % 8 || c_off % 8))) return -1;
+    if ((1 << l) == C / 4) lg_cg = l;
+  if (lg_cg < 0 || C % 4) return -1;
   const int OH = (up || dilate) ? 2 * H : H, OW = (up || dilate) ? 2 * W : W;
   const int Hq = OH + 2 * P, Wq = OW + 2 * P;
   const int rows = N * H, items = W << lg_cg;
@@ -28,10 +27,7 @@ extern "C" int fold_rows2_host(const float* dpad, int ctot, int c_off, int N, in
       float s_pw[12];
       const int np = fold_row_entry(f, OH, row % H, s_prow, s_pw);   // thread 0 between the two barriers
       for (int tid = 0; tid < nthreads; tid++)
-        for (int it = tid; it < items; it += nthreads) {
-          if (cv == 8) fold_item_t<8>(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc.data(), s_qw.data());
-          else fold_item_t<4>(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc.data(), s_qw.data());
-        }
+        for (int it = tid; it < items; it += nthreads) fold_item(f, lg_cg, Hq, Wq, row, it, np, s_prow, s_pw, s_pc.data(), s_qw.data());
     }
   }
   return 0;
