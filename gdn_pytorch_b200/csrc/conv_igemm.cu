@@ -1,6 +1,6 @@
 // Implicit-GEMM convolution for sm_100a: tcgen05.mma (BF16 x BF16 -> FP32 in TMEM), TMA-staged NHWC tiles.
 //
-// One persistent CTA per SM, 8 warps:
+// One persistent CTA per SM, 8 warps (12 with the second epilogue group):
 //   warps 0-3  epilogue  (TMEM -> registers -> bias / ReLU / residual / tanh / BN statistics -> global)
 //   warp  4    A producer (activations, TMA)
 //   warp  5    MMA issuer 0 (one elected thread) + TMEM owner
