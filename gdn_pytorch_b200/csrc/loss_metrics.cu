@@ -525,25 +525,60 @@ __device__ __forceinline__ MinMax metrics_load_mm(const MetricImg& w) {
   return mm;
 }
 
-// radix-select state after `passes` completed passes, recomputed by one thread per CTA from the global histograms
-// (<= 4 x 256 bins): value prefix, rank still to find, and the number of valid pixels (total of the first histogram)
+// radix-select state after `passes` completed passes, recomputed per CTA from the global histograms (<= 4 x 256 bins):
+// value prefix, rank still to find, and the number of valid pixels (total of the first histogram).
+// Called by a WHOLE WARP (all 32 lanes, every lane returns the same values): lane l holds bins 8l .. 8l+7, a shuffle scan
+// finds the lane whose cumulative count crosses the rank, that lane finds the bin.  The first version walked the bins with
+// one thread -- up to 255 dependent global loads per pass, which made it the critical path of every metrics kernel (34 us
+// for the first radix pass over 5 MB, +5 .. 18 us per further pass, 72 us for the final one:
+// profiles/r02r_ncu_metrics.summary.txt).  Integer arithmetic: same result as the sequential walk (bin 255 is never tested).
 __device__ void metrics_select_state(const MetricImg& w, int passes, int which, unsigned int& prefix, long long& k,
                                      long long& nvalid) {
-  long long n = 0;
-  for (int bin = 0; bin < 256; bin++) n += w.hist[0][0][bin];
+  const unsigned int full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned int s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += w.hist[0][0][lane * 8 + j];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(full, s, o);
+  const long long n = (long long)s;
   nvalid = n;
   prefix = 0;
-  k = n > 0 ? (n - 1) / 2 : 0;                  // lower median (torch.median), calculate_error.py:86 / :134 / :175
+  long long kk = n > 0 ? (n - 1) / 2 : 0;         // lower median (torch.median), calculate_error.py:86 / :134 / :175
   for (int ps = 0; ps < passes; ps++) {
     const int shift = 24 - 8 * ps;
-    unsigned int bin = 0;
-    for (; bin < 255; bin++) {
-      const long long c = w.hist[ps][which][bin];
-      if (k < c) break;
-      k -= c;
+    unsigned int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c[j] = w.hist[ps][which][lane * 8 + j];
+      tot += c[j];
+    }
+    unsigned int incl = tot;                       // inclusive prefix over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned int all = __shfl_sync(full, incl, 31), c255 = __shfl_sync(full, c[7], 31);
+    const unsigned int hit = __ballot_sync(full, kk < (long long)incl);
+    unsigned int bin;
+    if (hit == 0u) {                               // rank beyond the histogram: the sequential walk ends at bin 255
+      bin = 255u;
+      kk -= (long long)(all - c255);
+    } else {
+      const int L = __ffs(hit) - 1;                // first lane whose cumulative count exceeds the rank
+      long long myk = kk - (long long)(incl - tot);
+      int j = 0;
+      for (; j < 7; j++) {
+        if (myk < (long long)c[j]) break;
+        myk -= (long long)c[j];
+      }
+      bin = __shfl_sync(full, (unsigned int)(lane * 8 + j), L);
+      kk = __shfl_sync(full, myk, L);
     }
     prefix |= bin << shift;
   }
+  k = kk;
 }
 
 template <int VAR>
@@ -557,11 +592,11 @@ __global__ void __launch_bounds__(256) metrics_radix_kernel(const MetricK m, Met
   __shared__ unsigned int hist[2][256];
   __shared__ unsigned int s_prefix[2];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 64) {             // warp 0: ground truth, warp 1: prediction
     long long k, nv;
     unsigned int pf;
-    metrics_select_state(ws[b], pass, threadIdx.x, pf, k, nv);
-    s_prefix[threadIdx.x] = pf;
+    metrics_select_state(ws[b], pass, threadIdx.x >> 5, pf, k, nv);
+    if ((threadIdx.x & 31) == 0) s_prefix[threadIdx.x >> 5] = pf;
   }
   __syncthreads();
   const MinMax mm = metrics_load_mm(ws[b]);
@@ -594,12 +629,14 @@ __global__ void __launch_bounds__(256) metrics_final_kernel(const MetricK m, Met
   __shared__ float s_med[2];
   __shared__ long long s_n;
   __shared__ int s_last;
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 64) {             // warp 0: ground truth, warp 1: prediction
     long long k, nv;
     unsigned int pf;
-    metrics_select_state(ws[b], 4, threadIdx.x, pf, k, nv);
-    s_med[threadIdx.x] = __uint_as_float(pf);
-    if (threadIdx.x == 0) s_n = nv;
+    metrics_select_state(ws[b], 4, threadIdx.x >> 5, pf, k, nv);
+    if ((threadIdx.x & 31) == 0) {
+      s_med[threadIdx.x >> 5] = __uint_as_float(pf);
+      if (threadIdx.x == 0) s_n = nv;
+    }
   }
   __syncthreads();
   const long long nvalid = s_n;
