@@ -46,6 +46,8 @@ def _obj(ref):
 
 
 class EmulatedLib:
+    deterministic = 0      # set to 1 (before the engine is built) to emulate GDN_DETERMINISTIC=1: slab layout of the wgrads
+
     def __init__(self):
         self.calls = {}
         for name in dir(self):
@@ -76,7 +78,9 @@ class EmulatedLib:
         return 148
 
     def _e_deterministic(self):
-        return 0          # the emulator always reduces in a fixed order; the slab workspace is a property of the GPU kernels
+        # the emulator always reduces in a fixed order; with deterministic = 1 it reproduces the LAYOUT of the deterministic
+        # split-K (gdn_wgrad_desc.slabs / gdn_unpack_wgrad_slabs) so that the engine's plumbing is checked on the CPU
+        return int(self.deterministic)
 
     # ---- BatchNorm fold (eval)
     def _e_bn_fold(self, gamma, beta, rmean, rvar, eps, scale, bias, c, s):
@@ -350,6 +354,25 @@ class EmulatedLib:
         pt, pl = max(0, -ylo), max(0, -xlo)
         pb, pr = max(0, yhi - (Hp - 1)), max(0, xhi - (Wp - 1))
         Xn = F.pad(X.permute(0, 3, 1, 2), (pl, pr, pt, pb)).permute(0, 2, 3, 1)
+        if w.slabs:
+            # deterministic split-K: split s STORES its partial to slab s (no accumulation, dw untouched).  Emulated with
+            # min(max_slabs, 3, images) splits over the images; the count goes to *splits_used (host memory)
+            assert w.max_slabs >= 1 and bool(w.splits_used), "slabs need max_slabs and splits_used"
+            nsp = max(1, min(w.max_slabs, 3, n))
+            w.splits_used[0] = nsp
+            elems = w.kh * w.kw * cin * w.cout_pad
+            slabs = _t(w.slabs, (nsp, w.kh * w.kw, cin, w.cout_pad), torch.float32)
+            slabs.fill_(float("nan"))             # every element of every used slab must be written
+            bounds = [n * i // nsp for i in range(nsp + 1)]
+            for sp in range(nsp):
+                lo, hi = bounds[sp], bounds[sp + 1]
+                for r in range(w.kh):
+                    for q in range(w.kw):
+                        y0, x0 = ylo + pt + r, xlo + pl + q
+                        xs = Xn[lo:hi, y0: y0 + (w.out_h - 1) * st + 1: st, x0: x0 + (w.out_w - 1) * st + 1: st]
+                        slabs[sp, r * w.kw + q] = torch.einsum("nyxi,nyxo->io", xs, dy[lo:hi])
+            assert elems == slabs[0].numel()
+            return 0
         dw = _t(w.dw, (w.kh * w.kw, cin, w.cout_pad), torch.float32)
         for r in range(w.kh):
             for q in range(w.kw):
@@ -358,7 +381,19 @@ class EmulatedLib:
                 dw[r * w.kw + q] += torch.einsum("nyxi,nyxo->io", xs, dy)
         return 0
 
-    def _e_unpack_wgrad(self, pd, dw, grad, accumulate, s):
+    def _e_unpack_wgrad_slabs(self, pd, dw, slabs, slab_elems, grad, accumulate, s):
+        """sum `slabs` partial gradients lying slab_elems floats apart in index order, then scatter like gdn_unpack_wgrad"""
+        k = _obj(pd)
+        T = 1 if k.col_c else k.kh * k.kw
+        slab_elems = slab_elems.value if hasattr(slab_elems, "value") else slab_elems
+        assert slabs >= 1 and (slabs == 1 or slab_elems >= T * k.b_pad * k.a_pad)
+        tot = _t(dw, (T, k.b_pad, k.a_pad), torch.float32).clone()
+        for sl in range(1, slabs):
+            tot += _t(_addr(dw) + 4 * sl * slab_elems, (T, k.b_pad, k.a_pad), torch.float32)
+        assert torch.isfinite(tot).all(), "a slab element was never written"
+        return self._e_unpack_wgrad(pd, tot.data_ptr(), grad, accumulate, s, _keep=tot)
+
+    def _e_unpack_wgrad(self, pd, dw, grad, accumulate, s, _keep=None):
         k = _obj(pd)
         T = 1 if k.col_c else k.kh * k.kw
         src = _t(dw, (T, k.b_pad, k.a_pad), torch.float32)

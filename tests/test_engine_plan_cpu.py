@@ -204,3 +204,50 @@ def test_instance_norm_autoencoder_inference_plan(monkeypatch):
         engine_forward(eng, x)
         got = eng.depth()
     assert relerr(got, want) <= 1e-2, relerr(got, want)
+
+
+@pytest.mark.parametrize("switch", ["deterministic", "separate_finalize"])
+def test_training_plan_switches(switch, monkeypatch):
+    """two run-time switches of the training plan, on the emulated ABI: (a) GDN_DETERMINISTIC=1 -- the weight gradients go
+    through the slab workspace (gdn_wgrad_desc.slabs, gdn_unpack_wgrad_slabs) and no fill precedes them; (b)
+    GDN_FUSE_BNFIN=0 -- one gdn_bn_finalize launch per BatchNorm layer instead of the finalisation in the convolution tail.
+    Both must produce the parameter gradients of the default plan."""
+    from gdn_pytorch_b200.engine import Engine
+    from oracle import synth
+    from tests import minigraphs
+    from tests.abi_emulator import EmulatedLib
+
+    def grads(det, fuse_fin):
+        g = minigraphs.mini_rtod()
+        sd = minigraphs.synth_params(g, 0)
+        for k, v in sd.items():
+            if not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+        x = synth.synth_rgb(B, H, W, 1)
+        R = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(5)) - 0.5
+        monkeypatch.setattr(EmulatedLib, "deterministic", det)
+        monkeypatch.setenv("GDN_FUSE_BNFIN", "1" if fuse_fin else "0")
+        with emulated_abi() as emu:
+            eng = Engine(g, sd, B, H, W, train=True, backward=True, want=[u.out for u in g.units], device=torch.device("cpu"))
+            with torch.no_grad():
+                engine_forward(eng, x)
+                out = eng.depth()
+                eng.flat_grad.zero_()
+                eng.dpre.copy_((R * (1 - out * out)).view(B, H, W))
+                run_ops(eng.bwd)
+            return {k: v.clone() for k, v in eng.grad.items()}, dict(emu.calls), eng
+
+    ref, calls0, _ = grads(0, True)
+    assert "gdn_bn_finalize" not in calls0 and "gdn_unpack_wgrad_slabs" not in calls0
+    if switch == "deterministic":
+        got, calls, eng = grads(1, True)
+        assert eng.det and calls.get("gdn_unpack_wgrad_slabs", 0) == calls0["gdn_unpack_wgrad"] and "gdn_unpack_wgrad" not in calls
+        tol = 1e-5            # the slab sums add the same products in another order
+    else:
+        got, calls, eng = grads(0, False)
+        n_bn = sum(1 for u in eng.units if u.bn is not None)
+        assert calls.get("gdn_bn_finalize", 0) == n_bn and not any(cu.fin_fused for cu in eng.cu.values() if hasattr(cu, "fin"))
+        tol = 0.0             # same arithmetic, other launch
+    for k in ref:
+        assert (got[k] - ref[k]).abs().max().item() <= tol * max(1.0, ref[k].abs().max().item()), k
+
