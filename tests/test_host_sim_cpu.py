@@ -6,6 +6,7 @@ import os
 import shutil
 import subprocess
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -108,3 +109,53 @@ def test_pack_v2_host_simulation_matches_the_layout(case, kind):
                           C.c_void_p(out.data_ptr()), 96)
     assert tb in (16, 32, 64), tb
     assert torch.equal(out, full.to(torch.bfloat16))
+
+
+def test_lane_partitioned_radix_select_equals_the_sequential_walk():
+    """metrics_select_state (csrc/loss_metrics.cu) finds the histogram bin that holds rank k with one warp: lane l owns
+    bins 8l .. 8l+7, an inclusive scan over the lanes finds the first lane whose cumulative count exceeds k, that lane walks
+    its 8 bins (the last one untested).  This restates that partition in numpy and checks it against the sequential walk
+    over bins 0 .. 254 it replaced (bin 255 is the fall-through of both), incl. empty histograms, single-bin histograms,
+    everything in bin 255 and ranks beyond the total."""
+    def sequential(hist, k):
+        b = 0
+        while b < 255:
+            c = int(hist[b])
+            if k < c:
+                break
+            k -= c
+            b += 1
+        return b, k
+
+    def by_lanes(hist, k):
+        c = hist.reshape(32, 8).astype(np.int64)
+        tot = c.sum(1)
+        incl = np.cumsum(tot)
+        hit = k < incl
+        if not hit.any():
+            return 255, k - (int(incl[31]) - int(c[31, 7]))
+        lane = int(np.argmax(hit))
+        myk = k - int(incl[lane] - tot[lane])
+        j = 0
+        while j < 7:
+            if myk < c[lane, j]:
+                break
+            myk -= int(c[lane, j])
+            j += 1
+        return lane * 8 + j, myk
+
+    rng = np.random.RandomState(0)
+    for t in range(20000):
+        mode = t % 5
+        h = rng.randint(0, 50, 256)
+        if mode == 1:
+            h[rng.randint(0, 256, 200)] = 0
+        elif mode == 2:
+            h[:] = 0
+            h[rng.randint(0, 256)] = rng.randint(1, 1000)
+        elif mode == 3:
+            h[:255] = 0
+            h[255] = rng.randint(0, 5)
+        n = int(h.sum())
+        k = int(rng.randint(0, max(n, 1) + (3 if mode == 4 else 0))) if n > 0 else 0
+        assert sequential(h, k) == by_lanes(h, k), (mode, k)
